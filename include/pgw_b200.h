@@ -1,0 +1,248 @@
+/*
+ * pgw_b200.h -- C ABI of libpgw_b200.so, the sm_100a implementation of the
+ * PGW4ERA5 per-timestep path.
+ *
+ * Every entry point takes plain DEVICE pointers owned by the caller, sizes, a
+ * CUDA stream (passed as void*) and returns 0 or a negative host-side error
+ * (PGW_E_*).  Data-dependent failures that the reference reports as Python
+ * ValueErrors are accumulated on the device in a sticky 32-bit error word
+ * (PGW_ERR_* bits, atomicOr) that the caller reads back after the stream
+ * synchronises; the Python host layer maps the bits to the reference's
+ * messages.  Nothing here allocates device memory; workspaces are passed in.
+ *
+ * Layout: all fields are C-order with the horizontal index fastest, i.e.
+ * element (level k, column c) lives at k*ncol + c, ncol = nlat*nlon, exactly
+ * the (time, level, lat, lon) layout of the reference for one timestep.
+ *
+ * "Replaces" cites the reference (menschj/PGW4ERA5) interface each entry point
+ * stands in for.
+ */
+#ifndef PGW_B200_H
+#define PGW_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PGW_B200_ABI_VERSION 1
+
+/* host-side return codes */
+#define PGW_OK               0
+#define PGW_E_INVALID       -1   /* bad argument (null pointer, size, mode)      */
+#define PGW_E_LAUNCH        -2   /* CUDA launch / runtime error                 */
+#define PGW_E_SMEM          -3   /* column stash does not fit in shared memory  */
+
+/* device-side sticky error bits */
+#define PGW_ERR_SRC_NOT_ASCENDING   (1u << 0)  /* functions.py:500-501 */
+#define PGW_ERR_TARG_NOT_ASCENDING  (1u << 1)  /* functions.py:502-503 */
+#define PGW_ERR_EXTRAP_OFF          (1u << 2)  /* functions.py:564-566 */
+#define PGW_ERR_PS_HIST_RANGE       (1u << 4)  /* functions.py:360-361,363 */
+#define PGW_ERR_PREF_BELOW_SFC      (1u << 5)  /* functions.py:162-165 */
+#define PGW_ERR_PS_BOUND            (1u << 7)  /* ps left the range the column
+                                                  stash was sized for: rerun
+                                                  with a larger ps_bound */
+
+/* extrapolation modes of interp_extrap_1d, functions.py:516-520 */
+#define PGW_EXTRAP_OFF       0
+#define PGW_EXTRAP_LINEAR    1
+#define PGW_EXTRAP_CONSTANT  2
+#define PGW_EXTRAP_NAN       3
+
+#define PGW_MAX_SOIL   16
+#define PGW_MAX_ITER   64
+
+const char *pgw_version(void);
+const char *pgw_last_error(void);      /* text of the last PGW_E_LAUNCH */
+
+/* ------------------------------------------------------------------------
+ * Vertical log-pressure interpolation.
+ * Replaces interp_1d_for_timelatlon(orig_array, src_p, targ_p, interp_array,
+ * ntime, nlat, nlon, extrapolate), functions.py:479-508 (+ interp_extrap_1d
+ * :511-580), the reference's only compiled boundary, and the np.log calls of
+ * its caller interp_logp_4d, functions.py:469-475.
+ *   var   [nt, ks, ncol]   values on source levels
+ *   src_p [nt, ks, ncol]   source pressure, or [ks] if src_p_is_1d
+ *   targ_p[nt, kt, ncol]   target pressure
+ *   out   [nt, kt, ncol]
+ *   p_is_log: 0 = arrays hold pressure (log taken in-kernel),
+ *             1 = arrays already hold ln p (the numba signature).
+ *   err   device uint32, OR-ed with PGW_ERR_{SRC,TARG}_NOT_ASCENDING /
+ *         PGW_ERR_EXTRAP_OFF.
+ * ---------------------------------------------------------------------- */
+int pgw_interp_logp_f64(const double *var, const double *src_p, const double *targ_p,
+                        double *out, int nt, int ks, int kt, long long ncol,
+                        int src_p_is_1d, int p_is_log, int mode,
+                        uint32_t *err, void *stream);
+int pgw_interp_logp_f32(const float *var, const float *src_p, const float *targ_p,
+                        float *out, int nt, int ks, int kt, long long ncol,
+                        int src_p_is_1d, int p_is_log, int mode,
+                        uint32_t *err, void *stream);
+
+/* ------------------------------------------------------------------------
+ * Humidity conversions (IFS saturation vapour pressure over water and ice).
+ * Replace specific_to_relative_humidity(hus, pa, ta), functions.py:107-116 and
+ * relative_to_specific_humidity(hur, pa, ta), functions.py:118-125.
+ * Elementwise over n values.
+ * ---------------------------------------------------------------------- */
+int pgw_specific_to_relative_humidity_f32(const float *hus, const float *pa, const float *ta,
+                                          float *hur, long long n, void *stream);
+int pgw_relative_to_specific_humidity_f32(const float *hur, const float *pa, const float *ta,
+                                          float *hus, long long n, void *stream);
+int pgw_specific_to_relative_humidity_f64(const double *hus, const double *pa, const double *ta,
+                                          double *hur, long long n, void *stream);
+int pgw_relative_to_specific_humidity_f64(const double *hur, const double *pa, const double *ta,
+                                          double *hus, long long n, void *stream);
+
+/* ------------------------------------------------------------------------
+ * Hydrostatic geopotential at a reference pressure.
+ * Replaces integ_geopot(pa_hl, zgs, ta, hus, level1, p_ref), functions.py:128-189.
+ *   pa_hl [nlev+1, ncol] half-level pressure (index 0 = model top)
+ *   zgs   [ncol] surface geopotential;  ta, hus [nlev, ncol]
+ *   p_ref_field [ncol] or NULL (then the scalar p_ref is used)
+ *   phi_ref [ncol] float64 output
+ *   err: PGW_ERR_PREF_BELOW_SFC
+ * ---------------------------------------------------------------------- */
+int pgw_integ_geopot_f32(const float *pa_hl, const float *zgs, const float *ta, const float *hus,
+                         const float *p_ref_field, double p_ref, double *phi_ref,
+                         int nlev, long long ncol, uint32_t *err, void *stream);
+int pgw_integ_geopot_f64(const double *pa_hl, const double *zgs, const double *ta, const double *hus,
+                         const double *p_ref_field, double p_ref, double *phi_ref,
+                         int nlev, long long ncol, uint32_t *err, void *stream);
+
+/* ------------------------------------------------------------------------
+ * Land / sea-ice weighted blend of the ts and tos deltas.
+ * Replaces integrate_tos(tos_field, ts_field, land_frac, ice_frac),
+ * functions.py:1145-1186.  n values each.
+ * ---------------------------------------------------------------------- */
+int pgw_integrate_tos_f32(const float *tos, const float *ts, const float *land, const float *ice,
+                          float *out, long long n, void *stream);
+int pgw_integrate_tos_f64(const double *tos, const double *ts, const double *land, const double *ice,
+                          double *out, long long n, void *stream);
+
+/* ------------------------------------------------------------------------
+ * Two-point linear time interpolation of a delta field (the arithmetic of
+ * load_delta, functions.py:288-292 -> xarray .interp -> scipy interp1d):
+ *   out = (hi - lo) / x_hi * x_new + lo      (float64 math, float32 storage)
+ * and the time mean used for the deep-soil delta (step_03_apply_to_era.py:134-136).
+ * ---------------------------------------------------------------------- */
+int pgw_time_interp_f32(const float *lo, const float *hi, double x_hi, double x_new,
+                        float *out, long long n, void *stream);
+int pgw_time_mean_f32(const float *series, int ntime, float *out, long long n, void *stream);
+
+/* ------------------------------------------------------------------------
+ * The fused per-timestep pass.
+ * Replaces the body of pgw_for_era5(), step_03_apply_to_era.py:60-343 with
+ * i_reinterp = 0 and a scalar p_ref: pressures (:64-88), RELHUM (:91-94),
+ * sea-ice/skin/soil update (:103-146, integrate_tos), load_delta's time blend
+ * (functions.py:288-292), replace_delta_sfc + vert_interp_delta
+ * (functions.py:343-431) for ta,hur,ua,va, delta application (:158-173) and
+ * k_spec iterations of the surface-pressure fixed point (:182-319, integ_geopot
+ * and relative_to_specific_humidity inside).
+ *
+ * The stopping rule of the reference is field-global (:189,:308): iteration
+ * stops at the first N with max|phi error| <= thresh.  The kernel therefore
+ * runs exactly k_spec iterations for every column, records max|err_k| for
+ * k = 1..k_spec in maxerr[k-1] (float64 bits, atomicMax) and the trajectory
+ * dps_k in dps_traj, and writes PS/QV for dps_{k_spec}.  The caller then
+ *   - all-reduces maxerr (MAX) over ranks in latitude-band mode,
+ *   - calls pgw_timestep_finalize(), which finds N on the device and, if
+ *     N < k_spec, rewrites PS/QV for dps_N,
+ *   - reruns with a larger k_spec if maxerr[k_spec-1] > thresh.
+ * ---------------------------------------------------------------------- */
+typedef struct pgw_tslab {
+    const float *lo;    /* field at the delta stamp before the ERA5 time      */
+    const float *hi;    /* field at the stamp after (== lo for an exact hit)  */
+    double x_hi;        /* (t_after  - t_before) in ns, as xarray hands scipy  */
+    double x_new;       /* (t_target - t_before) in ns; 0 for an exact hit     */
+} pgw_tslab;
+
+typedef struct pgw_timestep_args {
+    /* sizes */
+    long long ncol;         /* nlat*nlon of this rank's band                   */
+    int nlev;               /* full model levels (137)                         */
+    int nplev;              /* GCM pressure levels K (<= 64)                   */
+    int nsoil;              /* soil levels (<= PGW_MAX_SOIL)                   */
+    int plev_descending;    /* 1: 3-D delta slabs are stored bottom-up
+                               (pressure descending, CMIP6 order)              */
+    /* level tables, DEVICE float64 */
+    const double *ak, *bk;      /* [nlev+1] */
+    const double *akm, *bkm;    /* [nlev]   */
+    const double *plev;         /* [nplev] in FILE order                       */
+    /* HOST copies of ak, bk ([nlev+1]); used to size the shared-memory stash  */
+    const double *ak_host, *bk_host;
+    /* ERA5 fields of one timestep, DEVICE float32 */
+    const float *PS, *FIS, *FR_LAND, *FR_SEA_ICE, *T_SKIN;   /* [ncol]         */
+    const float *T_SO;                                       /* [nsoil, ncol]  */
+    const float *T, *QV, *U, *V;                             /* [nlev, ncol]   */
+    /* climate deltas bracketing the ERA5 time */
+    pgw_tslab ta, hur, ua, va;          /* [nplev, ncol] each                  */
+    pgw_tslab tas, hurs, ps_hist, ts, tos, siconc;   /* [ncol]                 */
+    pgw_tslab zg_ref;                   /* zg delta on the p_ref level, [ncol] */
+    const float *ts_clim;               /* annual-mean ts delta [ncol]         */
+    double soil_decay[PGW_MAX_SOIL];    /* exp(-soil1/2.8)                     */
+    /* surface-pressure adjustment (settings.py:140-150) */
+    double p_ref;
+    double adj_factor;
+    double thresh_phi_ref_max_error;
+    int k_spec;             /* iterations to run (1..PGW_MAX_ITER)             */
+    double ps_bound;        /* upper bound of ps used to size the column stash */
+    /* outputs, DEVICE float32 (must not alias the inputs) */
+    float *PS_out, *T_SKIN_out, *FR_SEA_ICE_out;   /* [ncol]                   */
+    float *T_SO_out;                                /* [nsoil, ncol]            */
+    float *T_out, *QV_out, *U_out, *V_out;          /* [nlev, ncol]             */
+    float *dps_out;                                 /* [ncol] ps_pgw - PS       */
+    /* workspace */
+    float *dps_traj;        /* [k_spec, ncol]                                  */
+    uint64_t *maxerr;       /* [PGW_MAX_ITER] float64 bits, zeroed by the call */
+    float *stats;           /* [2]: min target p, min source p (ta/hur)        */
+    uint32_t *err;          /* sticky error word                               */
+} pgw_timestep_args;
+
+/* bytes of dynamic shared memory the column kernel needs for these args, or
+ * a negative PGW_E_* code */
+long long pgw_sizeof_timestep_args(void);   /* for FFI layout checks */
+long long pgw_timestep_smem_bytes(const pgw_timestep_args *a);
+int pgw_timestep(const pgw_timestep_args *a, void *stream);
+
+/* device-side result of the convergence scan, written by finalize */
+typedef struct pgw_timestep_result {
+    int n_iter;             /* N = first k with maxerr[k-1] <= thresh, or 0    */
+    int converged;          /* 1 if N found within k_spec                      */
+    int rewritten;          /* 1 if PS/QV were rewritten for N < k_spec        */
+    int reserved;
+} pgw_timestep_result;
+
+int pgw_timestep_finalize(const pgw_timestep_args *a, pgw_timestep_result *result_dev,
+                          void *stream);
+
+/* ------------------------------------------------------------------------
+ * step_02: bilinear regridding and annual-cycle smoothing.
+ * pgw_regrid_bilinear_f32 replaces the two scipy interp1d passes of
+ * regrid_lat_lon(), functions.py:859 and :892, including the pole rows
+ * (:833-842, zonal mean of the nearest row) and the periodic longitude
+ * (:866-874) which are applied through index tables instead of concatenation:
+ *   src [nfield, ny_s, nx_s]  ->  dst [nfield, ny_t, nx_t]
+ *   j0,j1 [ny_t] source rows (-1 = south-pole row, -2 = north-pole row,
+ *                i.e. the zonal mean of row 0 / ny_s-1), wy [ny_t] weight of j1
+ *   i0,i1 [nx_t] source columns (already wrapped), wx [nx_t] weight of i1
+ *   polemean [nfield, 2] zonal means (filled by pgw_zonal_mean_f32)
+ * pgw_smooth_harmonic_f32 replaces filter_data()/harmonic_ac_analysis(),
+ * functions.py:606-740: per grid point mean + 3 harmonics of the nt-long series.
+ * ---------------------------------------------------------------------- */
+int pgw_zonal_mean_f32(const float *src, float *polemean, long long nfield, int ny_s, int nx_s,
+                       void *stream);
+int pgw_regrid_bilinear_f32(const float *src, float *dst, const float *polemean,
+                            long long nfield, int ny_s, int nx_s, int ny_t, int nx_t,
+                            const int *j0, const int *j1, const double *wy,
+                            const int *i0, const int *i1, const double *wx,
+                            void *stream);
+int pgw_smooth_harmonic_f32(const float *series, float *out, int nt, long long npoint,
+                            void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PGW_B200_H */

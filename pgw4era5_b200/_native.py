@@ -1,0 +1,109 @@
+"""
+ctypes binding of libpgw_b200.so (include/pgw_b200.h).
+
+There is no CPU fallback: if the shared library is missing or cannot be loaded
+the import of this module raises, and every operator in this package with it.
+``python -m pgw4era5_b200.build`` (or ``__graft_entry__.build()``) compiles it
+with nvcc for sm_100a.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpgw_b200.so")
+
+PGW_MAX_SOIL = 16
+PGW_MAX_ITER = 64
+
+PGW_OK, PGW_E_INVALID, PGW_E_LAUNCH, PGW_E_SMEM = 0, -1, -2, -3
+
+ERR_SRC_NOT_ASCENDING = 1 << 0
+ERR_TARG_NOT_ASCENDING = 1 << 1
+ERR_EXTRAP_OFF = 1 << 2
+ERR_PS_HIST_RANGE = 1 << 4
+ERR_PREF_BELOW_SFC = 1 << 5
+ERR_PS_BOUND = 1 << 7
+
+EXTRAP_MODES = {"off": 0, "linear": 1, "constant": 2, "nan": 3}
+
+c_fp = C.c_void_p   # device pointers travel as plain addresses
+
+
+class TSlab(C.Structure):
+    _fields_ = [("lo", c_fp), ("hi", c_fp), ("x_hi", C.c_double), ("x_new", C.c_double)]
+
+
+class TimestepArgs(C.Structure):
+    _fields_ = (
+        [("ncol", C.c_longlong), ("nlev", C.c_int), ("nplev", C.c_int), ("nsoil", C.c_int),
+         ("plev_descending", C.c_int)]
+        + [(n, c_fp) for n in ("ak", "bk", "akm", "bkm", "plev", "ak_host", "bk_host")]
+        + [(n, c_fp) for n in ("PS", "FIS", "FR_LAND", "FR_SEA_ICE", "T_SKIN", "T_SO", "T", "QV", "U", "V")]
+        + [(n, TSlab) for n in ("ta", "hur", "ua", "va", "tas", "hurs", "ps_hist", "ts", "tos",
+                                "siconc", "zg_ref")]
+        + [("ts_clim", c_fp), ("soil_decay", C.c_double * PGW_MAX_SOIL),
+           ("p_ref", C.c_double), ("adj_factor", C.c_double),
+           ("thresh_phi_ref_max_error", C.c_double), ("k_spec", C.c_int), ("ps_bound", C.c_double)]
+        + [(n, c_fp) for n in ("PS_out", "T_SKIN_out", "FR_SEA_ICE_out", "T_SO_out", "T_out", "QV_out",
+                               "U_out", "V_out", "dps_out", "dps_traj", "maxerr", "stats", "err")]
+    )
+
+
+class TimestepResult(C.Structure):
+    _fields_ = [("n_iter", C.c_int), ("converged", C.c_int), ("rewritten", C.c_int), ("reserved", C.c_int)]
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "libpgw_b200.so not found at %s: build it with `python -m pgw4era5_b200.build` "
+            "(nvcc, sm_100a).  This package has no CPU fallback." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    ll, i, d, vp = C.c_longlong, C.c_int, C.c_double, C.c_void_p
+    sig = {
+        "pgw_version": (C.c_char_p, []),
+        "pgw_last_error": (C.c_char_p, []),
+        "pgw_sizeof_timestep_args": (ll, []),
+        "pgw_interp_logp_f64": (i, [vp, vp, vp, vp, i, i, i, ll, i, i, i, vp, vp]),
+        "pgw_interp_logp_f32": (i, [vp, vp, vp, vp, i, i, i, ll, i, i, i, vp, vp]),
+        "pgw_specific_to_relative_humidity_f32": (i, [vp, vp, vp, vp, ll, vp]),
+        "pgw_relative_to_specific_humidity_f32": (i, [vp, vp, vp, vp, ll, vp]),
+        "pgw_specific_to_relative_humidity_f64": (i, [vp, vp, vp, vp, ll, vp]),
+        "pgw_relative_to_specific_humidity_f64": (i, [vp, vp, vp, vp, ll, vp]),
+        "pgw_integ_geopot_f32": (i, [vp, vp, vp, vp, vp, d, vp, i, ll, vp, vp]),
+        "pgw_integ_geopot_f64": (i, [vp, vp, vp, vp, vp, d, vp, i, ll, vp, vp]),
+        "pgw_integrate_tos_f32": (i, [vp, vp, vp, vp, vp, ll, vp]),
+        "pgw_integrate_tos_f64": (i, [vp, vp, vp, vp, vp, ll, vp]),
+        "pgw_time_interp_f32": (i, [vp, vp, d, d, vp, ll, vp]),
+        "pgw_time_mean_f32": (i, [vp, i, vp, ll, vp]),
+        "pgw_timestep_smem_bytes": (ll, [C.POINTER(TimestepArgs)]),
+        "pgw_timestep": (i, [C.POINTER(TimestepArgs), vp]),
+        "pgw_timestep_finalize": (i, [C.POINTER(TimestepArgs), vp, vp]),
+        "pgw_zonal_mean_f32": (i, [vp, vp, ll, i, i, vp]),
+        "pgw_regrid_bilinear_f32": (i, [vp, vp, vp, ll, i, i, i, i, vp, vp, vp, vp, vp, vp, vp]),
+        "pgw_smooth_harmonic_f32": (i, [vp, vp, i, ll, vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    if lib.pgw_sizeof_timestep_args() != C.sizeof(TimestepArgs):
+        raise ImportError("pgw_timestep_args layout mismatch: C %d vs ctypes %d"
+                          % (lib.pgw_sizeof_timestep_args(), C.sizeof(TimestepArgs)))
+    return lib, sorted(sig)
+
+
+lib, EXPORTED = _load()
+
+
+def check(rc, what):
+    """Raise for a negative host-side return code."""
+    if rc == PGW_OK:
+        return
+    msg = lib.pgw_last_error().decode() if rc in (PGW_E_LAUNCH, PGW_E_SMEM) else ""
+    name = {PGW_E_INVALID: "invalid argument", PGW_E_LAUNCH: "CUDA error", PGW_E_SMEM:
+            "shared memory"}.get(rc, "error %d" % rc)
+    raise NativeError("%s: %s %s" % (what, name, msg))

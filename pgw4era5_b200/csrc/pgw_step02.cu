@@ -1,0 +1,169 @@
+// step_02 kernels of libpgw_b200 (sm_100a): bilinear regridding of GCM deltas
+// to the ERA5 grid (regrid_lat_lon, functions.py:748-898) and the spectral
+// smoothing of daily annual cycles (filter_data / harmonic_ac_analysis,
+// functions.py:606-740).  Both are pure streaming: regridding is write-bound
+// (a 1 degree source field fits in L2, the 0.25 degree target is 16x larger),
+// smoothing reads and writes every series once.
+#include "pgw_common.cuh"
+
+namespace pgw {
+
+// zonal mean of the first and last source row of every field: the values the
+// reference puts on the synthetic pole rows (functions.py:833-842)
+__global__ void __launch_bounds__(128)
+zonal_mean_kernel(const float *__restrict__ src, float *__restrict__ polemean, long long nfield, int ny_s,
+                  int nx_s) {
+    const long long f = blockIdx.x;
+    const int which = blockIdx.y;                   // 0: row 0, 1: row ny_s-1
+    const float *row = src + (f * ny_s + (which ? ny_s - 1 : 0)) * (long long)nx_s;
+    double s = 0.0;
+    for (int i = threadIdx.x; i < nx_s; i += blockDim.x) s += (double)row[i];
+    __shared__ double part[4];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += part[w];
+        polemean[f * 2 + which] = (float)(t / (double)nx_s);
+    }
+}
+
+__device__ __forceinline__ double src_at(const float *fld, const float *pm, int j, int i, int nx_s) {
+    if (j == -1) return (double)pm[0];
+    if (j == -2) return (double)pm[1];
+    return (double)__ldg(fld + (long long)j * nx_s + i);
+}
+
+// one thread = VEC consecutive target longitudes of one (field, target row)
+template <int VEC>
+__global__ void __launch_bounds__(256)
+regrid_kernel(const float *__restrict__ src, float *__restrict__ dst, const float *__restrict__ polemean,
+              long long nfield, int ny_s, int nx_s, int ny_t, int nx_t, const int *__restrict__ j0,
+              const int *__restrict__ j1, const double *__restrict__ wy, const int *__restrict__ i0,
+              const int *__restrict__ i1, const double *__restrict__ wx) {
+    const int nxv = nx_t / VEC;
+    const long long total = nfield * ny_t * (long long)nxv;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int iv = (int)(idx % nxv);
+        const long long r = idx / nxv;
+        const int jt = (int)(r % ny_t);
+        const long long f = r / ny_t;
+        const float *fld = src + f * ny_s * (long long)nx_s;
+        const float *pm = polemean + f * 2;
+        const int ja = j0[jt], jb = j1[jt];
+        const double wj = wy[jt];
+        float res[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            const int it = iv * VEC + v;
+            const int ia = i0[it], ib = i1[it];
+            // latitude pass (functions.py:859), then longitude pass (:892)
+            const double a0 = src_at(fld, pm, ja, ia, nx_s), a1 = src_at(fld, pm, jb, ia, nx_s);
+            const double b0 = src_at(fld, pm, ja, ib, nx_s), b1 = src_at(fld, pm, jb, ib, nx_s);
+            const double a = (a1 - a0) * wj + a0;
+            const double b = (b1 - b0) * wj + b0;
+            res[v] = (float)((b - a) * wx[it] + a);
+        }
+        float *o = dst + (f * ny_t + jt) * (long long)nx_t + (long long)iv * VEC;
+        if (VEC == 4) __stcs(reinterpret_cast<float4 *>(o), make_float4(res[0], res[1], res[2], res[3]));
+        else {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) __stcs(o + v, res[v]);
+        }
+    }
+}
+
+// harmonic_ac_analysis (functions.py:678-740): mean + harmonics 1..3 of an
+// nt-long series per grid point.  One thread per grid point, lanes = adjacent
+// points; cos/sin tables for the three harmonics are staged in shared memory.
+__global__ void __launch_bounds__(128)
+smooth_kernel(const float *__restrict__ series, float *__restrict__ out, int nt, long long npoint) {
+    extern __shared__ double tab[];                 // [nt][6]: cos1 sin1 cos2 sin2 cos3 sin3
+    for (int t = threadIdx.x; t < nt; t += blockDim.x) {
+        for (int k = 1; k <= 3; ++k) {
+            const double br = 2. * 3.141592653589793 * k / (double)nt * (double)(t + 1);   // :726
+            tab[t * 6 + 2 * (k - 1)] = cos(br);
+            tab[t * 6 + 2 * (k - 1) + 1] = sin(br);
+        }
+    }
+    __syncthreads();
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npoint;
+         p += (long long)gridDim.x * blockDim.x) {
+        double sum = 0.0, a1 = 0, b1 = 0, a2 = 0, b2 = 0, a3 = 0, b3 = 0;
+        bool bad = false;
+        for (int t = 0; t < nt; ++t) {
+            const float xf = __ldcs(series + (long long)t * npoint + p);
+            bad |= isnan(xf);
+            const double x = (double)xf;
+            const double *tb = tab + t * 6;
+            sum += x;
+            a1 = fma(x, tb[0], a1); b1 = fma(x, tb[1], b1);
+            a2 = fma(x, tb[2], a2); b2 = fma(x, tb[3], b2);
+            a3 = fma(x, tb[4], a3); b3 = fma(x, tb[5], b3);
+        }
+        const double sc = 2. / (double)nt;
+        const double mean = sum / (double)nt;
+        a1 *= sc; b1 *= sc; a2 *= sc; b2 *= sc; a3 *= sc; b3 *= sc;
+        for (int t = 0; t < nt; ++t) {
+            const double *tb = tab + t * 6;
+            // sum(hcts[0:3]) + mean, functions.py:739 (python sum starts at 0)
+            const double h = ((0.0 + (a1 * tb[0] + b1 * tb[1])) + (a2 * tb[2] + b2 * tb[3])) +
+                             (a3 * tb[4] + b3 * tb[5]);
+            __stcs(out + (long long)t * npoint + p, bad ? NAN : (float)(h + mean));
+        }
+    }
+}
+
+}  // namespace pgw
+
+using namespace pgw;
+
+extern "C" {
+
+int pgw_zonal_mean_f32(const float *src, float *polemean, long long nfield, int ny_s, int nx_s, void *stream) {
+    if (!src || !polemean || nfield <= 0 || ny_s < 1 || nx_s < 1) return PGW_E_INVALID;
+    if (nfield > 2147483647LL) return PGW_E_INVALID;
+    zonal_mean_kernel<<<dim3((unsigned)nfield, 2), 128, 0, (cudaStream_t)stream>>>(src, polemean, nfield, ny_s, nx_s);
+    return pgw_check_launch("zonal_mean_kernel");
+}
+
+int pgw_regrid_bilinear_f32(const float *src, float *dst, const float *polemean, long long nfield, int ny_s,
+                            int nx_s, int ny_t, int nx_t, const int *j0, const int *j1, const double *wy,
+                            const int *i0, const int *i1, const double *wx, void *stream) {
+    if (!src || !dst || !polemean || !j0 || !j1 || !wy || !i0 || !i1 || !wx) return PGW_E_INVALID;
+    if (nfield <= 0 || ny_s < 1 || nx_s < 1 || ny_t < 1 || nx_t < 1) return PGW_E_INVALID;
+    const bool vec = (nx_t % 4 == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+    const long long total = nfield * ny_t * (long long)(vec ? nx_t / 4 : nx_t);
+    long long g = (total + 255) / 256;
+    const long long cap = 148LL * 32;
+    if (g > cap) g = cap;
+    if (vec)
+        regrid_kernel<4><<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(src, dst, polemean, nfield, ny_s, nx_s,
+                                                                         ny_t, nx_t, j0, j1, wy, i0, i1, wx);
+    else
+        regrid_kernel<1><<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(src, dst, polemean, nfield, ny_s, nx_s,
+                                                                         ny_t, nx_t, j0, j1, wy, i0, i1, wx);
+    return pgw_check_launch("regrid_kernel");
+}
+
+int pgw_smooth_harmonic_f32(const float *series, float *out, int nt, long long npoint, void *stream) {
+    if (!series || !out || nt < 8 || npoint <= 0) return PGW_E_INVALID;     // i < floor(nt/2) for i=1..3
+    const size_t smem = sizeof(double) * 6 * (size_t)nt;
+    if (smem > 200 * 1024) return PGW_E_SMEM;
+    static thread_local size_t configured = 48 * 1024;
+    if (smem > configured) {
+        if (cudaFuncSetAttribute(smooth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return pgw_check_launch("cudaFuncSetAttribute(smooth_kernel)");
+        configured = smem;
+    }
+    long long g = (npoint + 127) / 128;
+    const long long cap = 148LL * 8;
+    if (g > cap) g = cap;
+    smooth_kernel<<<(unsigned)g, 128, smem, (cudaStream_t)stream>>>(series, out, nt, npoint);
+    return pgw_check_launch("smooth_kernel");
+}
+
+}  // extern "C"

@@ -1,0 +1,342 @@
+"""
+Device-resident PGW engine: the host side of the fused per-timestep pass.
+
+``DeltaSet`` keeps the GCM climate-delta climatology in HBM (uploaded or
+NCCL-broadcast once; it is time invariant), ``PGWEngine`` applies it to one
+ERA5 timestep per call through ``pgw_timestep`` / ``pgw_timestep_finalize`` of
+libpgw_b200.so.  This replaces the body of the reference's ``pgw_for_era5``
+(step_03_apply_to_era.py:44-381) between reading and writing the file; names
+of fields follow ``settings.var_name_map``.
+
+The reference's stopping rule is field-global (step_03_apply_to_era.py:189,308).
+The kernel runs a speculative number of iterations ``k_spec`` for every column
+and records max|error| per iteration; ``finalize`` finds the reference's count N
+on the device.  N == k_spec: nothing to do.  N < k_spec: PS/QV are rewritten for
+iteration N.  Not converged within k_spec: the timestep is rerun with
+``max_n_iter - 1`` iterations (the reference raises once ``it > max_n_iter``).
+``k_spec`` follows the last N, which is stable from one timestep to the next.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _native as N
+from . import settings, timeinterp
+
+VARS_3D = ("ta", "hur", "ua", "va", "zg")
+VARS_2D = ("tas", "hurs", "ps_hist", "ts", "tos", "siconc")
+
+_STATUS_BYTES = 8 * N.PGW_MAX_ITER + 16 + 8 + 8     # maxerr | result | stats | err,pad
+
+MSG_TOP = ("ERA5 top pressure is lower than climate delta top pressure. If you are certain that "
+           "you do not need the data beyond to upper-most pressure level of the climate delta, "
+           "you can set the flag --ignore_top_pressure_error and re-run the script.")
+MSG_PREF = ("p_ref locally lies below the surface. Please set a lower reference pressue "
+            "(p_ref_inp) in settings.py")
+MSG_NOCONV = ('ERROR! Pressure adjustment did not converge for file {}. Consider increasing the '
+              'value for "max_n_iter" in settings.py')
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class DeltaSet:
+    """
+    Climate deltas resident on one GPU.
+
+    ``deltas``: var -> dict(time=datetime64[nt], plev=[K] or None, data=[nt,(K),ny,nx])
+    for ta, hur, ua, va, zg, tas, hurs, ts, tos, siconc (SCEN-HIST) and ``ps_hist``
+    (the HIST ps climatology, functions.py:330-332).  29 February is dropped
+    once here (functions.py:224-230).
+    """
+
+    def __init__(self, deltas, device="cuda"):
+        self.device = torch.device(device)
+        self.vars = {}
+        for name in VARS_3D + VARS_2D:
+            if name not in deltas:
+                raise KeyError("climate delta %r missing" % name)
+            d = deltas[name]
+            stamps = np.asarray(d["time"]).astype("datetime64[ns]")
+            keep = timeinterp.drop_leap_day(stamps)
+            data = d["data"]
+            if not isinstance(data, torch.Tensor):
+                data = torch.as_tensor(np.asarray(data))
+            if len(keep) != len(stamps):
+                data = data[torch.as_tensor(keep, device=data.device)]
+            data = data.to(self.device, torch.float32).contiguous()
+            plev = None if d.get("plev") is None else np.asarray(d["plev"], dtype=np.float64)
+            self.vars[name] = dict(time=stamps[keep], plev=plev, data=data)
+        self.shape2d = tuple(self.vars["ts"]["data"].shape[-2:])
+        self.ncol = self.shape2d[0] * self.shape2d[1]
+        plev = self.vars["ta"]["plev"]
+        for name in ("hur", "ua", "va"):
+            if not np.array_equal(self.vars[name]["plev"], plev):
+                raise ValueError("ta, hur, ua, va deltas must share their pressure levels")
+        self.plev = plev
+        desc = bool(plev[0] > plev[-1])
+        mono = np.all(np.diff(plev) < 0) if desc else np.all(np.diff(plev) > 0)
+        if not mono:
+            raise ValueError("Source pressure values must be ascending!")
+        self.plev_descending = desc
+        self.plev_dev = torch.as_tensor(plev, device=self.device, dtype=torch.float64)
+        self._brackets = {}
+        self.ts_clim = None
+        self.refresh_derived()
+
+    def refresh_derived(self):
+        """Annual mean of the ts delta (step_03_apply_to_era.py:134-136), computed once."""
+        ts = self.vars["ts"]["data"]
+        self.ts_clim = torch.empty(ts.shape[1:], device=self.device, dtype=torch.float32)
+        N.check(N.lib.pgw_time_mean_f32(_ptr(ts), ts.shape[0], _ptr(self.ts_clim), self.ncol, _stream()),
+                "pgw_time_mean_f32")
+
+    def tensors(self):
+        """All device tensors in a fixed order (for the NCCL broadcast)."""
+        return [self.vars[n]["data"] for n in VARS_3D + VARS_2D]
+
+    def bracket(self, name, when):
+        key = (name, when)
+        b = self._brackets.get(key)
+        if b is None:
+            if len(self._brackets) > 4096:
+                self._brackets.clear()
+            b = timeinterp.bracket(self.vars[name]["time"], when)
+            self._brackets[key] = b
+        return b
+
+    def slab(self, name, when, level=None):
+        """pgw_tslab for variable ``name`` at ERA5 time ``when`` (optionally one plev)."""
+        b = self.bracket(name, when)
+        data = self.vars[name]["data"]
+        lo, hi = data[b.ind_before], data[b.ind_after]
+        if level is not None:
+            lo, hi = lo[level], hi[level]
+        return N.TSlab(lo.data_ptr(), hi.data_ptr(), b.x_hi, b.x_new)
+
+
+class Pending:
+    """A submitted timestep; ``result()`` waits for it and applies the host-side checks."""
+
+    def __init__(self, engine, args, out, status_host, event, ctx):
+        self.engine, self.args, self.out = engine, args, out
+        self.status_host, self.event, self.ctx = status_host, event, ctx
+        self._done = None
+
+    def result(self):
+        if self._done is None:
+            self._done = self.engine._complete(self)
+        return self._done
+
+
+class PGWEngine:
+    """
+    ak, bk: half-level hybrid coefficients [L+1] (index 0 = model top); akm/bkm
+    optional full-level coefficients (else the reference's mid-point rule,
+    step_03_apply_to_era.py:68-85); soil1: soil depths [S].
+    """
+
+    def __init__(self, ak, bk, deltas, soil1=(), akm=None, bkm=None, ps_bound=110000.0, group=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("PGWEngine needs a CUDA device (B200, sm_100a); there is no CPU path")
+        self.deltas = deltas
+        self.device = deltas.device
+        ak = np.asarray(ak)
+        bk = np.asarray(bk)
+        if akm is None:
+            akm = 0.5 * np.diff(ak) + ak[:-1]
+            bkm = 0.5 * np.diff(bk) + bk[:-1]
+        self.ak = np.ascontiguousarray(ak, dtype=np.float64)
+        self.bk = np.ascontiguousarray(bk, dtype=np.float64)
+        self.akm = np.ascontiguousarray(akm, dtype=np.float64)
+        self.bkm = np.ascontiguousarray(bkm, dtype=np.float64)
+        self.nlev = len(self.akm)
+        dev = lambda a: torch.as_tensor(a, device=self.device, dtype=torch.float64)
+        self.ak_d, self.bk_d, self.akm_d, self.bkm_d = dev(self.ak), dev(self.bk), dev(self.akm), dev(self.bkm)
+        soil1 = np.asarray(soil1)
+        if len(soil1) > N.PGW_MAX_SOIL:
+            raise ValueError("at most %d soil levels" % N.PGW_MAX_SOIL)
+        self.soil_decay = np.exp(-soil1 / 2.8).astype(np.float64)     # step_03:140
+        self.ps_bound = float(ps_bound)
+        self.group = group
+        self.k_pred = 8
+        self._ws = {}
+        self.stats = dict(timesteps=0, rewrites=0, reruns=0)
+
+    # ------------------------------------------------------------------ workspace
+    def _workspace(self, ncol, max_iter):
+        key = (ncol, max_iter)
+        ws = self._ws.get(key)
+        if ws is None:
+            ws = dict(
+                traj=torch.empty((max_iter, ncol), device=self.device, dtype=torch.float32),
+                status=torch.zeros(_STATUS_BYTES, device=self.device, dtype=torch.uint8),
+            )
+            self._ws = {key: ws}
+        return ws
+
+    def alloc_outputs(self, ny, nx, nsoil):
+        e = lambda *s: torch.empty(s, device=self.device, dtype=torch.float32)
+        L = self.nlev
+        return dict(PS=e(1, ny, nx), T_SKIN=e(1, ny, nx), FR_SEA_ICE=e(1, ny, nx), T_SO=e(1, nsoil, ny, nx),
+                    T=e(1, L, ny, nx), QV=e(1, L, ny, nx), U=e(1, L, ny, nx), V=e(1, L, ny, nx),
+                    delta_ps=e(1, ny, nx))
+
+    # ------------------------------------------------------------------ submit
+    def submit(self, era, era_step_dt, out=None, ignore_top_pressure_error=False, k_spec=None,
+               file_name="<memory>"):
+        """
+        Enqueue one timestep on the current CUDA stream.  ``era``: float32 CUDA
+        tensors PS, FIS, FR_LAND, FR_SEA_ICE, T_SKIN [1,ny,nx], T_SO [1,S,ny,nx],
+        T, QV, U, V [1,L,ny,nx] (the names of settings.var_name_map).  Returns a
+        ``Pending``; nothing is synchronised here.
+        """
+        if settings.i_reinterp:
+            raise NotImplementedError("i_reinterp = 1 is not on the CUDA path (SURVEY.md 8f, rank 2)")
+        if settings.p_ref_inp is None:
+            raise NotImplementedError("p_ref_inp = None is not on the CUDA path (SURVEY.md 8f, rank 2)")
+        ds = self.deltas
+        ny, nx = era["PS"].shape[-2:]
+        ncol = ny * nx
+        if ncol != ds.ncol:
+            raise ValueError("Lat dimension of input files is inconsistent!" if ny != ds.shape2d[0]
+                             else "Lon dimension of input files is inconsistent!")
+        L = self.nlev
+        nsoil = len(self.soil_decay)
+        f = {}
+        for name, lev in (("PS", 1), ("FIS", 1), ("FR_LAND", 1), ("FR_SEA_ICE", 1), ("T_SKIN", 1),
+                          ("T_SO", nsoil), ("T", L), ("QV", L), ("U", L), ("V", L)):
+            if lev == 0:
+                continue
+            t = era[name]
+            if t.device != self.device or t.dtype != torch.float32 or not t.is_contiguous():
+                t = t.to(self.device, torch.float32).contiguous()
+            if t.numel() != lev * ncol:
+                raise ValueError("field %s has %d values, expected %d" % (name, t.numel(), lev * ncol))
+            f[name] = t
+        if out is None:
+            out = self.alloc_outputs(ny, nx, nsoil)
+        max_iter = int(settings.max_n_iter)
+        k_max = max(1, min(max_iter - 1, N.PGW_MAX_ITER))
+        if k_spec is None:
+            k_spec = self.k_pred
+        k_spec = max(1, min(int(k_spec), k_max))
+        ws = self._workspace(ncol, k_max)
+        status = ws["status"]
+
+        zg = ds.vars["zg"]
+        sel = np.nonzero(zg["plev"] == float(settings.p_ref_inp))[0]      # .sel(plev=p_ref), step_03:294
+        if len(sel) != 1:
+            raise KeyError(float(settings.p_ref_inp))
+
+        a = N.TimestepArgs()
+        a.ncol, a.nlev, a.nplev, a.nsoil = ncol, L, len(ds.plev), nsoil
+        a.plev_descending = int(ds.plev_descending)
+        a.ak, a.bk, a.akm, a.bkm = (self.ak_d.data_ptr(), self.bk_d.data_ptr(), self.akm_d.data_ptr(),
+                                    self.bkm_d.data_ptr())
+        a.plev = ds.plev_dev.data_ptr()
+        a.ak_host, a.bk_host = self.ak.ctypes.data, self.bk.ctypes.data
+        for name in ("PS", "FIS", "FR_LAND", "FR_SEA_ICE", "T_SKIN", "T", "QV", "U", "V"):
+            setattr(a, name, f[name].data_ptr())
+        a.T_SO = f["T_SO"].data_ptr() if nsoil else 0
+        for name in ("ta", "hur", "ua", "va", "tas", "hurs", "ps_hist", "ts", "tos", "siconc"):
+            setattr(a, name, ds.slab(name, era_step_dt))
+        a.zg_ref = ds.slab("zg", era_step_dt, level=int(sel[0]))
+        a.ts_clim = ds.ts_clim.data_ptr()
+        for i, v in enumerate(self.soil_decay):
+            a.soil_decay[i] = float(v)
+        a.p_ref = float(settings.p_ref_inp)
+        a.adj_factor = float(settings.adj_factor)
+        a.thresh_phi_ref_max_error = float(settings.thresh_phi_ref_max_error)
+        a.k_spec = k_spec
+        a.ps_bound = self.ps_bound
+        a.PS_out, a.T_SKIN_out, a.FR_SEA_ICE_out = (out["PS"].data_ptr(), out["T_SKIN"].data_ptr(),
+                                                    out["FR_SEA_ICE"].data_ptr())
+        a.T_SO_out = out["T_SO"].data_ptr() if nsoil else 0
+        a.T_out, a.QV_out, a.U_out, a.V_out = (out["T"].data_ptr(), out["QV"].data_ptr(),
+                                               out["U"].data_ptr(), out["V"].data_ptr())
+        a.dps_out = out["delta_ps"].data_ptr()
+        a.dps_traj = ws["traj"].data_ptr()
+        base = status.data_ptr()
+        a.maxerr = base
+        a.stats = base + 8 * N.PGW_MAX_ITER + 16
+        a.err = base + 8 * N.PGW_MAX_ITER + 24
+        result_ptr = base + 8 * N.PGW_MAX_ITER
+
+        status[8 * N.PGW_MAX_ITER + 24:].zero_()                          # clear the sticky error word
+        st = _stream()
+        N.check(N.lib.pgw_timestep(C.byref(a), st), "pgw_timestep")
+        if self.group is not None:
+            # latitude-band mode: the stopping rule is global over all bands
+            import torch.distributed as dist
+            maxerr = status[:8 * N.PGW_MAX_ITER].view(torch.float64)
+            dist.all_reduce(maxerr, op=dist.ReduceOp.MAX, group=self.group)
+        N.check(N.lib.pgw_timestep_finalize(C.byref(a), C.c_void_p(result_ptr), st), "pgw_timestep_finalize")
+        host = torch.empty(_STATUS_BYTES, dtype=torch.uint8, pin_memory=True)
+        host.copy_(status, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        ctx = dict(era=era, when=era_step_dt, ignore_top=ignore_top_pressure_error, k_spec=k_spec,
+                   k_max=k_max, keep=(f, a), file_name=file_name)
+        return Pending(self, a, out, host, ev, ctx)
+
+    # ------------------------------------------------------------------ completion
+    def _complete(self, p):
+        p.event.synchronize()
+        raw = p.status_host.numpy()
+        nmi = N.PGW_MAX_ITER
+        maxerr = raw[:8 * nmi].view(np.float64)
+        n_iter, converged, rewritten, _ = raw[8 * nmi:8 * nmi + 16].view(np.int32)
+        min_targ_p, min_src_p = raw[8 * nmi + 16:8 * nmi + 24].view(np.float32)
+        err = int(raw[8 * nmi + 24:8 * nmi + 28].view(np.uint32)[0])
+        ctx = p.ctx
+        if self.group is not None:
+            err, min_targ_p, min_src_p = self._merge_status(err, min_targ_p, min_src_p)
+        if err & N.ERR_PS_HIST_RANGE:
+            raise ValueError()                                           # functions.py:360-361
+        if (min_targ_p < min_src_p or min_targ_p < float(np.min(self.deltas.plev))) \
+                and not ctx["ignore_top"]:
+            raise ValueError(MSG_TOP)                                    # functions.py:417-425
+        if err & N.ERR_PREF_BELOW_SFC:
+            raise ValueError(MSG_PREF)                                   # functions.py:162-165
+        if err & N.ERR_PS_BOUND:
+            self.ps_bound *= 1.25
+            self.stats["reruns"] += 1
+            return self.submit(ctx["era"], ctx["when"], out=p.out, ignore_top_pressure_error=ctx["ignore_top"],
+                               k_spec=ctx["k_spec"], file_name=ctx["file_name"]).result()
+        if not converged:
+            if ctx["k_spec"] >= ctx["k_max"]:
+                raise ValueError(MSG_NOCONV.format(ctx["file_name"]))   # step_03:315-319
+            self.stats["reruns"] += 1
+            return self.submit(ctx["era"], ctx["when"], out=p.out, ignore_top_pressure_error=ctx["ignore_top"],
+                               k_spec=ctx["k_max"], file_name=ctx["file_name"]).result()
+        self.k_pred = int(n_iter)
+        self.stats["timesteps"] += 1
+        self.stats["rewrites"] += int(rewritten)
+        res = dict(p.out)
+        res["n_iter"] = int(n_iter)
+        res["phi_max_errors"] = [float(x) for x in maxerr[:int(n_iter)]]
+        if settings.i_debug >= 2:
+            for it, e in enumerate(res["phi_max_errors"], 1):
+                print("### iteration {:03d}, phi max error: {}".format(it, e))
+        return res
+
+    def _merge_status(self, err, min_targ_p, min_src_p):
+        import torch.distributed as dist
+        bits = torch.tensor([(err >> i) & 1 for i in range(32)], device=self.device, dtype=torch.int32)
+        dist.all_reduce(bits, op=dist.ReduceOp.MAX, group=self.group)
+        mins = torch.tensor([min_targ_p, min_src_p], device=self.device, dtype=torch.float32)
+        dist.all_reduce(mins, op=dist.ReduceOp.MIN, group=self.group)
+        err = int(sum(int(b) << i for i, b in enumerate(bits.tolist())))
+        m = mins.tolist()
+        return err, m[0], m[1]
+
+    def apply(self, era, era_step_dt, **kw):
+        """Synchronous form of ``submit``: returns the output dict (device tensors)."""
+        return self.submit(era, era_step_dt, **kw).result()
