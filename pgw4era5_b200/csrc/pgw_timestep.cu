@@ -19,108 +19,130 @@
 //   functions.py:118-125, 128-189    hus from RH, geopotential integration
 #include "pgw_common.cuh"
 
+#include <cuda_pipeline.h>
+
 namespace pgw {
 
-__device__ __forceinline__ float blend_f32(const pgw_tslab &s, float w, long long off) {
-    const float lo = __ldg(s.lo + off);
-    if (w == 0.0f) return lo;
-    const float hi = __ldg(s.hi + off);
-    return fmaf(w, hi - lo, lo);
-}
-
-// scipy interp1d._call_linear with x = [0, x_hi]: slope * x_new + y_lo
-__device__ __forceinline__ double blend_f64(const pgw_tslab &s, long long off) {
+// scipy interp1d._call_linear with x = [0, x_hi]: slope * x_new + y_lo (float64)
+__device__ __forceinline__ double blend_f64(const pgw_tslab &s, uint32_t off) {
     const double lo = (double)__ldg(s.lo + off);
     if (s.x_new == 0.0) return lo;
     const double hi = (double)__ldg(s.hi + off);
     return (hi - lo) / s.x_hi * s.x_new + lo;
 }
 
-// Downward merge walk over the (pressure-ascending) source nodes of one pair of
-// variables.  Invariant after advance(p): lo < 0 (target above the first node),
-// or p_lo <= p and (hi is virtual or p < p_hi).
+__device__ __forceinline__ float fast_rcp(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float fast_lg2(float x) {
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float fast_ex2(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+// MUFU.RCP64H: >= 20 good bits of 1/x in one instruction
+__device__ __forceinline__ double rcp64_approx(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    return r;
+}
+
+// ln(pb/pt), pb >= pt > 0, float64 accuracy ~1e-13 relative for s < 0.06 (all
+// adjacent ERA5 half levels below ~100 hPa): 2 atanh(s), s = (pb-pt)/(pb+pt).
+__device__ __forceinline__ double ln_ratio(double pb, double pt) {
+    const double d = pb - pt;
+    const double sm = pb + pt;
+    double r = rcp64_approx(sm);
+    r = fma(r, fma(-sm, r, 1.0), r);            // one Newton step: ~1e-12
+    const double s = d * r;
+    if (s > 0.06) return log(pb / pt);          // coarse layers: exact path
+    const double s2 = s * s;
+    double poly = fma(s2, 2.0 / 9.0, 2.0 / 7.0);
+    poly = fma(s2, poly, 2.0 / 5.0);
+    poly = fma(s2, poly, 2.0 / 3.0);
+    poly = fma(s2, poly, 2.0);
+    return s * poly;
+}
+
+// Downward merge walk over the pressure-ascending source nodes of one pair of
+// variables (interp_extrap_1d in 'constant' mode, functions.py:511-580).
+// State: lo node (index, pressure, values) and the differences to the hi node.
+// inv_w == 0 encodes "no interpolation": at/after the last node, or (after the
+// walk has passed node 0) before the first node; then the lo values are returned.
 struct Walk2 {
-    int lo;
-    bool hi_virtual;
-    float p_lo, p_hi, inv_w;
-    float a_lo, a_hi, a_nx;
-    float b_lo, b_hi, b_nx;
+    int lo;                 // index of the lo node; -1 once the target is above node 0
+    float p_lo, inv_p_lo, inv_w;
+    float a_lo, a_d, a_nx;  // value at lo, (hi - lo), prefetched value of node lo-1
+    float b_lo, b_d, b_nx;
 };
 
-struct ColumnCtx {
-    const pgw_timestep_args *a;
-    const float *s_plev;     // ascending
-    long long c;
-    float wa, wb;            // time weights of the two variables of a pair
-};
+struct Tslab32 { const float *lo, *hi; float w; };
 
-__device__ __forceinline__ void load_node(const pgw_timestep_args &a, const pgw_tslab &va, float wa,
-                                          const pgw_tslab &vb, float wb, int j, long long c,
-                                          float &xa, float &xb) {
-    const int fj = a.plev_descending ? (a.nplev - 1 - j) : j;
-    const long long off = (long long)fj * a.ncol + c;
-    xa = blend_f32(va, wa, off);
-    xb = blend_f32(vb, wb, off);
+__device__ __forceinline__ float node_value(const Tslab32 &s, uint32_t off) {
+    const float lo = __ldg(s.lo + off);
+    if (s.w == 0.0f) return lo;
+    return fmaf(s.w, __ldg(s.hi + off) - lo, lo);
 }
 
-__device__ __forceinline__ void walk_advance(Walk2 &w, float p, const pgw_timestep_args &a,
-                                             const pgw_tslab &va, float wa, const pgw_tslab &vb,
-                                             float wb, const float *s_plev, long long c) {
-    while (w.lo >= 0 && w.p_lo > p) {
-        w.p_hi = w.p_lo; w.a_hi = w.a_lo; w.b_hi = w.b_lo; w.hi_virtual = false;
-        --w.lo;
-        if (w.lo >= 0) {
-            w.p_lo = s_plev[w.lo];
-            w.a_lo = w.a_nx; w.b_lo = w.b_nx;
-            if (w.lo >= 1) load_node(a, va, wa, vb, wb, w.lo - 1, c, w.a_nx, w.b_nx);
-            w.inv_w = __frcp_rn(__log2f(__fdividef(w.p_hi, w.p_lo)));
-        }
-    }
-}
-
-// interp_extrap_1d, 'constant' mode (functions.py:511-580)
-__device__ __forceinline__ void walk_eval(const Walk2 &w, float p, float &xa, float &xb) {
-    if (w.lo < 0) { xa = w.a_hi; xb = w.b_hi; }                       // below first node
-    else if (w.hi_virtual || p == w.p_lo) { xa = w.a_lo; xb = w.b_lo; } // beyond last / exact
-    else {
-        const float t = __log2f(__fdividef(p, w.p_lo)) * w.inv_w;
-        xa = fmaf(t, w.a_hi - w.a_lo, w.a_lo);
-        xb = fmaf(t, w.b_hi - w.b_lo, w.b_lo);
-    }
-}
-
-constexpr int kU = 4;   // levels per register batch (double-buffered)
+constexpr int kRing = 6;     // levels in flight per thread (cp.async ring, +1 spare slot)
 
 template <int NT>
 __global__ void __launch_bounds__(NT)
 pgw_column_kernel(const __grid_constant__ pgw_timestep_args a, const int lst, const int np) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int L = a.nlev, K = a.nplev;
-    double *s_ak = reinterpret_cast<double *>(smem);
-    double *s_bk = s_ak + (L + 1);
-    double *s_akm = s_bk + (L + 1);
-    double *s_bkm = s_akm + L;
-    double *st_T = s_bkm + L;                                  // [np][NT] T_pgw (float64)
+    // ---- shared memory carve-up
+    double2 *s_hl = reinterpret_cast<double2 *>(smem);                  // [L+1] (ak, bk)
+    double *st_T = reinterpret_cast<double *>(s_hl + (L + 1));          // [np][NT] T_pgw
     float *st_e = reinterpret_cast<float *>(st_T + (size_t)np * NT);   // [np][NT] e_pgw
-    float *s_akmf = st_e + (size_t)np * NT;
-    float *s_bkmf = s_akmf + L;
-    float *s_plev = s_bkmf + L;                                // [K] ascending pressure
+    float *ring = st_e + (size_t)np * NT;                              // [kRing+1][4][NT]
+    float2 *s_m = reinterpret_cast<float2 *>(ring + (size_t)(kRing + 1) * 4 * NT);   // [L] (akm, bkm)
+    float *s_plev = reinterpret_cast<float *>(s_m + L);                 // [K] ascending
+    float *s_inv_plev = s_plev + K;                                     // [K]
+    float *s_inv_w = s_inv_plev + K;                                    // [K] 1/log2(p[j+1]/p[j])
 
     const int tid = threadIdx.x;
-    for (int i = tid; i <= L; i += NT) { s_ak[i] = a.ak[i]; s_bk[i] = a.bk[i]; }
-    for (int i = tid; i < L; i += NT) {
-        const double am = a.akm[i], bm = a.bkm[i];
-        s_akm[i] = am; s_bkm[i] = bm; s_akmf[i] = (float)am; s_bkmf[i] = (float)bm;
+    for (int i = tid; i <= L; i += NT) s_hl[i] = make_double2(a.ak[i], a.bk[i]);
+    for (int i = tid; i < L; i += NT) s_m[i] = make_float2((float)a.akm[i], (float)a.bkm[i]);
+    for (int i = tid; i < K; i += NT) {
+        const int f0 = a.plev_descending ? (K - 1 - i) : i;
+        const float p0 = (float)a.plev[f0];
+        s_plev[i] = p0;
+        s_inv_plev[i] = 1.0f / p0;
+        if (i + 1 < K) {
+            const float p1 = (float)a.plev[a.plev_descending ? (K - 2 - i) : (i + 1)];
+            s_inv_w[i] = 1.0f / log2f(p1 / p0);
+        } else s_inv_w[i] = 0.0f;
     }
-    for (int i = tid; i < K; i += NT)
-        s_plev[i] = (float)a.plev[a.plev_descending ? (K - 1 - i) : i];
     __syncthreads();
 
-    const long long n = a.ncol;
-    long long c = (long long)blockIdx.x * NT + tid;
+    const uint32_t n = (uint32_t)a.ncol;
+    uint32_t c = blockIdx.x * NT + tid;
     const bool active = c < n;
     if (!active) c = n - 1;          // compute redundantly, never store
     unsigned errbits = 0;
+
+    // ---- async ring: this thread's T, QV, U, V of one level per slot
+    float *my_ring = ring + tid;
+    auto prefetch = [&](int l) {
+        if (l >= 0) {
+            float *dst = my_ring + (size_t)(l % (kRing + 1)) * 4 * NT;
+            const uint32_t off = (uint32_t)l * n + c;
+            __pipeline_memcpy_async(dst, a.T + off, 4);
+            __pipeline_memcpy_async(dst + NT, a.QV + off, 4);
+            __pipeline_memcpy_async(dst + 2 * NT, a.U + off, 4);
+            __pipeline_memcpy_async(dst + 3 * NT, a.V + off, 4);
+        }
+        __pipeline_commit();
+    };
+#pragma unroll
+    for (int i = 0; i < kRing; ++i) prefetch(L - 1 - i);
 
     // ---------------- surface, skin and soil (step_03:103-146) ----------------
     const float ps_f = __ldg(a.PS + c);
@@ -143,22 +165,23 @@ pgw_column_kernel(const __grid_constant__ pgw_timestep_args a, const int lst, co
             a.T_SKIN_out[c] = (float)((double)__ldg(a.T_SKIN + c) + comb);
             for (int s = 0; s < a.nsoil; ++s) {
                 const double dso = clim + a.soil_decay[s] * (comb - clim);
-                a.T_SO_out[(long long)s * n + c] =
-                    (float)((double)__ldg(a.T_SO + (long long)s * n + c) + dso);
+                a.T_SO_out[(uint32_t)s * n + c] = (float)((double)__ldg(a.T_SO + (uint32_t)s * n + c) + dso);
             }
         }
     }
 
     // ---------------- delta walkers (functions.py:343-431) ----------------
-    const float w_ta = (a.ta.x_new == 0.0) ? 0.0f : (float)(a.ta.x_new / a.ta.x_hi);
-    const float w_hur = (a.hur.x_new == 0.0) ? 0.0f : (float)(a.hur.x_new / a.hur.x_hi);
-    const float w_ua = (a.ua.x_new == 0.0) ? 0.0f : (float)(a.ua.x_new / a.ua.x_hi);
-    const float w_va = (a.va.x_new == 0.0) ? 0.0f : (float)(a.va.x_new / a.va.x_hi);
+    const auto tw = [](const pgw_tslab &s) { return (s.x_new == 0.0) ? 0.0f : (float)(s.x_new / s.x_hi); };
+    const Tslab32 v_ta{a.ta.lo, a.ta.hi, tw(a.ta)}, v_hur{a.hur.lo, a.hur.hi, tw(a.hur)};
+    const Tslab32 v_ua{a.ua.lo, a.ua.hi, tw(a.ua)}, v_va{a.va.lo, a.va.hi, tw(a.va)};
+    const auto node_off = [&](int j) -> uint32_t {
+        return (uint32_t)(a.plev_descending ? (K - 1 - j) : j) * n + c;
+    };
 
     Walk2 wA, wB;
     {
-        // replace_delta_sfc: node s carries (ps_hist, surface delta); nodes above it
-        // (in pressure) all hold the surface delta, so they never matter.
+        // replace_delta_sfc: node s carries (ps_hist, surface delta); the nodes after it all
+        // hold the surface delta, so node s acts as the last node of the column.
         const float psh = (float)blend_f64(a.ps_hist, c);
         int s = K - 1;
         if (!(psh > s_plev[K - 1])) {
@@ -167,114 +190,158 @@ pgw_column_kernel(const __grid_constant__ pgw_timestep_args a, const int lst, co
                 if (s_plev[k] < psh) { s = k; break; }
         }
         if (s < 0) { errbits |= PGW_ERR_PS_HIST_RANGE; s = 0; }
-        wA.lo = s; wA.hi_virtual = true; wA.p_lo = psh; wA.p_hi = psh; wA.inv_w = 0.0f;
-        wA.a_lo = (float)blend_f64(a.tas, c);
-        wA.b_lo = (float)blend_f64(a.hurs, c);
-        wA.a_hi = wA.a_lo; wA.b_hi = wA.b_lo; wA.a_nx = wA.a_lo; wA.b_nx = wA.b_lo;
-        if (s >= 1) load_node(a, a.ta, w_ta, a.hur, w_hur, s - 1, c, wA.a_nx, wA.b_nx);
+        wA.lo = s; wA.p_lo = psh; wA.inv_p_lo = fast_rcp(psh); wA.inv_w = 0.0f;
+        wA.a_lo = (float)blend_f64(a.tas, c); wA.a_d = 0.0f;
+        wA.b_lo = (float)blend_f64(a.hurs, c); wA.b_d = 0.0f;
+        wA.a_nx = wA.a_lo; wA.b_nx = wA.b_lo;
+        if (s >= 1) { wA.a_nx = node_value(v_ta, node_off(s - 1)); wA.b_nx = node_value(v_hur, node_off(s - 1)); }
 
-        wB.lo = K - 1; wB.hi_virtual = true; wB.p_lo = s_plev[K - 1]; wB.p_hi = wB.p_lo; wB.inv_w = 0.0f;
-        load_node(a, a.ua, w_ua, a.va, w_va, K - 1, c, wB.a_lo, wB.b_lo);
-        wB.a_hi = wB.a_lo; wB.b_hi = wB.b_lo; wB.a_nx = wB.a_lo; wB.b_nx = wB.b_lo;
-        if (K >= 2) load_node(a, a.ua, w_ua, a.va, w_va, K - 2, c, wB.a_nx, wB.b_nx);
+        wB.lo = K - 1; wB.p_lo = s_plev[K - 1]; wB.inv_p_lo = s_inv_plev[K - 1]; wB.inv_w = 0.0f;
+        wB.a_lo = node_value(v_ua, node_off(K - 1)); wB.a_d = 0.0f;
+        wB.b_lo = node_value(v_va, node_off(K - 1)); wB.b_d = 0.0f;
+        wB.a_nx = node_value(v_ua, node_off(K - 2)); wB.b_nx = node_value(v_va, node_off(K - 2));
     }
     float min_src_p = (wA.lo == 0) ? wA.p_lo : s_plev[0];
 
+    // advance a walker until p_lo <= p (or the first node has been passed)
+    auto advance = [&](Walk2 &w, float p, const Tslab32 &va, const Tslab32 &vb, bool synth_top) {
+        while (w.lo >= 0 && w.p_lo > p) {
+            const float hi_p = w.p_lo, hi_a = w.a_lo, hi_b = w.b_lo;
+            const bool from_synth = synth_top && (hi_p != s_plev[w.lo]);   // leaving the (ps_hist, sfc) node
+            --w.lo;
+            if (w.lo >= 0) {
+                w.p_lo = s_plev[w.lo]; w.inv_p_lo = s_inv_plev[w.lo];
+                w.a_lo = w.a_nx; w.b_lo = w.b_nx;
+                w.a_d = hi_a - w.a_lo; w.b_d = hi_b - w.b_lo;
+                w.inv_w = from_synth ? fast_rcp(fast_lg2(hi_p * w.inv_p_lo)) : s_inv_w[w.lo];
+                if (w.lo >= 1) { w.a_nx = node_value(va, node_off(w.lo - 1)); w.b_nx = node_value(vb, node_off(w.lo - 1)); }
+            } else {
+                // above node 0: constant extrapolation with node 0's values (they are in hi_*)
+                w.a_lo = hi_a; w.b_lo = hi_b; w.a_d = 0.0f; w.b_d = 0.0f; w.inv_w = 0.0f;
+            }
+        }
+    };
+
     const double pref = a.p_ref;
-    double pb_era = fma(PSd, s_bk[L], s_ak[L]);
+    double pb_era = fma(PSd, s_hl[L].y, s_hl[L].x);
     double acc_era = 0.0;
     if (pb_era < pref) errbits |= PGW_ERR_PREF_BELOW_SFC;
+    float psn_f = ps_f;                  // ps used for QV; replaced after the iteration
 
-    // One model level: RELHUM of the ERA state, interpolated deltas, PGW state.
-    // Returns e_pgw (vapour pressure of the PGW state, iteration invariant).
-    auto level = [&](int l, float t, float q, float u, float v, double &Tp, float &e_pgw) {
-        const float p = fmaf(ps_f, s_bkmf[l], s_akmf[l]);
-        walk_advance(wA, p, a, a.ta, w_ta, a.hur, w_hur, s_plev, c);
-        walk_advance(wB, p, a, a.ua, w_ua, a.va, w_va, s_plev, c);
-        float dta, dhur, dua, dva;
-        walk_eval(wA, p, dta, dhur);
-        walk_eval(wB, p, dua, dva);
+    // One model level: deltas at p, RH of the ERA state, PGW state, outputs T/U/V.
+    // Returns tm273 + dta pieces through Tp (float64 T_pgw) and e_pgw.
+    auto level = [&](int l, float t, float q, float u, float v, float &dta_out, float &e_pgw) {
+        const float2 m = s_m[l];
+        const float p = fmaf(ps_f, m.y, m.x);
+        if (wA.p_lo > p) advance(wA, p, v_ta, v_hur, true);
+        if (wB.p_lo > p) advance(wB, p, v_ua, v_va, false);
+        const float l2b = fast_lg2(p * wB.inv_p_lo);
+        const float l2a = (wA.inv_p_lo == wB.inv_p_lo) ? l2b : fast_lg2(p * wA.inv_p_lo);
+        const float tA = l2a * wA.inv_w, tB = l2b * wB.inv_w;
+        // t == 0: exact node hit or constant extrapolation -> the node value itself (NaN-safe)
+        const float dta = (tA == 0.0f) ? wA.a_lo : fmaf(tA, wA.a_d, wA.a_lo);
+        const float dhur = (tA == 0.0f) ? wA.b_lo : fmaf(tA, wA.b_d, wA.b_lo);
+        const float dua = (tB == 0.0f) ? wB.a_lo : fmaf(tB, wB.a_d, wB.a_lo);
+        const float dva = (tB == 0.0f) ? wB.b_lo : fmaf(tB, wB.b_d, wB.b_lo);
+
+        // saturation vapour pressure of the ERA and the PGW state (functions.py:74-105);
+        // T - 273.16 is formed from the exact T - 273 so that T_pgw is never rounded to fp32
         const float tm273 = t - 273.0f;
-        const float e_era = __fdividef(q * p, 0.622f + 0.378f * q);          // functions.py:58-64
-        const float rh_pgw = __fdividef(100.0f * e_era, esat_fast(tm273, 0.0f)) + dhur;
-        e_pgw = rh_pgw * 0.01f * esat_fast(tm273, dta);                      // functions.py:123
-        Tp = (double)t + (double)dta;
+        const float dTe = tm273 - 0.16f, tkp = tm273 + dta, dTp = tm273 + (dta - 0.16f);
+        const bool we = dTe >= 0.0f, wp = dTp >= 0.0f;
+        const float ce = we ? (273.0f - 32.19f) : (273.0f + 0.7f), cp = wp ? (273.0f - 32.19f) : (273.0f + 0.7f);
+        const float ae = we ? (17.502f * 1.4426950408889634f) : (22.587f * 1.4426950408889634f);
+        const float ap = wp ? (17.502f * 1.4426950408889634f) : (22.587f * 1.4426950408889634f);
+        const float de = tm273 + ce, dp = tkp + cp;
+        const float rr = fast_rcp(de * dp);                   // one reciprocal for both states
+        float es_e = 611.21f * fast_ex2(ae * dTe * (rr * dp));
+        float es_p = 611.21f * fast_ex2(ap * dTp * (rr * de));
+        if (!(dTe >= 0.0f || dTe <= -23.0f)) {                // mixed phase (or NaN): blend water/ice
+            const float ew = 611.21f * __expf(__fdividef(17.502f * dTe, tm273 + (273.0f - 32.19f)));
+            const float r = (dTe + 23.0f) * (1.0f / 23.0f), al = r * r;
+            es_e = al * ew + (1.0f - al) * es_e;
+        }
+        if (!(dTp >= 0.0f || dTp <= -23.0f)) {
+            const float ew = 611.21f * __expf(__fdividef(17.502f * dTp, tkp + (273.0f - 32.19f)));
+            const float r = (dTp + 23.0f) * (1.0f / 23.0f), al = r * r;
+            es_p = al * ew + (1.0f - al) * es_p;
+        }
+        // RELHUM of the ERA state (functions.py:107-116) + delta, back to vapour pressure (:123)
+        const float rh_pgw = fmaf(100.0f * q * p, fast_rcp((0.622f + 0.378f * q) * es_e), dhur);
+        e_pgw = rh_pgw * 0.01f * es_p;
+        dta_out = dta;
         if (active) {
-            const long long off = (long long)l * n + c;
-            st_stream(a.T_out + off, (float)Tp);
+            const uint32_t off = (uint32_t)l * n + c;
+            st_stream(a.T_out + off, t + dta);     // == (float)((double)t + (double)dta)
             st_stream(a.U_out + off, u + dua);
             st_stream(a.V_out + off, v + dva);
         }
     };
 
-    auto load_batch = [&](int l0, int l_end, float *t, float *q, float *u, float *v) {
-#pragma unroll
-        for (int i = 0; i < kU; ++i) {
-            const int l = l0 - i;
-            if (l >= l_end) {
-                const long long off = (long long)l * n + c;
-                t[i] = ld_stream(a.T + off); q[i] = ld_stream(a.QV + off);
-                u[i] = ld_stream(a.U + off); v[i] = ld_stream(a.V + off);
-            }
-        }
-    };
-
     // ---------------- phase 1: surface .. p_ref, parked in shared memory ----------------
-    {
-        float t0[kU], q0[kU], u0[kU], v0[kU], t1[kU], q1[kU], u1[kU], v1[kU];
-        load_batch(L - 1, lst, t0, q0, u0, v0);
-        for (int l0 = L - 1; l0 >= lst; l0 -= kU) {
-            load_batch(l0 - kU, lst, t1, q1, u1, v1);
-#pragma unroll
-            for (int i = 0; i < kU; ++i) {
-                const int l = l0 - i;
-                if (l >= lst) {
-                    double Tp; float e_pgw;
-                    level(l, t0[i], q0[i], u0[i], v0[i], Tp, e_pgw);
-                    st_T[(size_t)(l - lst) * NT + tid] = Tp;
-                    st_e[(size_t)(l - lst) * NT + tid] = e_pgw;
-                    // geopotential of the ERA state (functions.py:128-189)
-                    const double pt = fma(PSd, s_bk[l], s_ak[l]);
-                    const double tv = (double)t0[i] * (1.0 + 0.61 * (double)q0[i]);
-                    const double pte = fmin(fmax(pt, pref), pb_era);
-                    acc_era = fma(tv, log_ratio(pb_era, pte), acc_era);
-                    pb_era = pt;
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < kU; ++i) { t0[i] = t1[i]; q0[i] = q1[i]; u0[i] = u1[i]; v0[i] = v1[i]; }
+    for (int l = L - 1; l >= lst; --l) {
+        __pipeline_wait_prior(kRing - 1);
+        const float *slot = my_ring + (size_t)(l % (kRing + 1)) * 4 * NT;
+        const float t = slot[0], q = slot[NT], u = slot[2 * NT], v = slot[3 * NT];
+        prefetch(l - kRing);
+        float dta, e_pgw;
+        level(l, t, q, u, v, dta, e_pgw);
+        st_T[(l - lst) * NT + tid] = (double)t + (double)dta;
+        st_e[(l - lst) * NT + tid] = e_pgw;
+        // geopotential of the ERA state (functions.py:128-189)
+        const double2 hl = s_hl[l];
+        const double pt = fma(PSd, hl.y, hl.x);
+        if (pb_era >= pref) {
+            const double tv = (double)t * (1.0 + 0.61 * (double)q);
+            acc_era = fma(tv, ln_ratio(pb_era, pt > pref ? pt : pref), acc_era);
         }
+        pb_era = pt;
     }
     const double fis = (double)__ldg(a.FIS + c);
     const double phi_era = fis + kRd * acc_era;
-    const double gdzg = blend_f64(a.zg_ref, c) * kG;                 // step_03:292-295
-    const double t_low = st_T[(size_t)(L - 1 - lst) * NT + tid];    // ta_pgw on the lowest level
+    const double gdzg = blend_f64(a.zg_ref, c) * kG;              // step_03:292-295
+    const double t_low = st_T[(L - 1 - lst) * NT + tid];         // ta_pgw on the lowest level
+    const double2 hl_sfc = s_hl[L];
 
     // ---------------- phase 2: surface-pressure fixed point (step_03:182-319) ----------------
+    // The loads of the upper column are already in flight and overlap this phase.
     double dps = 0.0, adj = 0.0, psn = PSd;
     for (int k = 0; k < a.k_spec; ++k) {
         dps += adj;
         psn = PSd + dps;
-        if (active) a.dps_traj[(long long)k * n + c] = (float)dps;
+        psn_f = (float)psn;
+        if (active) a.dps_traj[(uint32_t)k * n + c] = (float)dps;
         if (psn > a.ps_bound) errbits |= PGW_ERR_PS_BOUND;
-        double pb = fma(psn, s_bk[L], s_ak[L]);
+        double pb = fma(psn, hl_sfc.y, hl_sfc.x);
         if (pb < pref) errbits |= PGW_ERR_PREF_BELOW_SFC;
         double acc = 0.0;
-        for (int l = L - 1; l >= lst; --l) {
-            const double pt = fma(psn, s_bk[l], s_ak[l]);
-            const float pf = (float)fma(psn, s_bkm[l], s_akm[l]);
-            const float e = st_e[(size_t)(l - lst) * NT + tid];
-            const double Td = st_T[(size_t)(l - lst) * NT + tid];
-            const float hus = __fdividef(0.622f * e, pf - 0.378f * e);      // functions.py:66-72
-            const double tv = fma(Td, 0.61 * (double)hus, Td);
-            const double pte = fmin(fmax(pt, pref), pb);
-            acc = fma(tv, log_ratio(pb, pte), acc);
+        int l = L - 1;
+#pragma unroll 4
+        for (; l >= lst; --l) {
+            const double2 hl = s_hl[l];
+            const double pt = fma(psn, hl.y, hl.x);
+            if (pt < pref) break;                                  // partial layer below
+            const float2 m = s_m[l];
+            const float e = st_e[(l - lst) * NT + tid];
+            const double Td = st_T[(l - lst) * NT + tid];
+            // Tv = T (1 + 0.61 hus), hus = 0.622 e / (p - 0.378 e)   (functions.py:66-72, :144)
+            const float g = fast_rcp(fmaf(-0.378f, e, fmaf(psn_f, m.y, m.x)));
+            const double tv = fma(Td, (double)((0.61f * 0.622f) * e * g), Td);
+            acc = fma(tv, ln_ratio(pb, pt), acc);
             pb = pt;
+        }
+        if (l >= lst && pb >= pref) {                              // layer that contains p_ref (:174-179)
+            const float2 m = s_m[l];
+            const float e = st_e[(l - lst) * NT + tid];
+            const double Td = st_T[(l - lst) * NT + tid];
+            const float g = fast_rcp(fmaf(-0.378f, e, fmaf(psn_f, m.y, m.x)));
+            const double tv = fma(Td, (double)((0.61f * 0.622f) * e * g), Td);
+            acc = fma(tv, ln_ratio(pb, pref), acc);
         }
         const double phi_pgw = fis + kRd * acc;
         const double err = (phi_pgw - phi_era) - gdzg;
         adj = -a.adj_factor * psn / (kRd * t_low) * err;
-        double ae = (active && !isnan(err)) ? fabs(err) : 0.0;          // max skips NaN (step_03:308)
+        double ae = (active && !isnan(err)) ? fabs(err) : 0.0;     // max skips NaN (step_03:308)
         ae = warp_max(ae);
         if ((tid & 31) == 0 && ae > 0.0)
             atomicMax(reinterpret_cast<unsigned long long *>(a.maxerr + k),
@@ -282,40 +349,32 @@ pgw_column_kernel(const __grid_constant__ pgw_timestep_args a, const int lst, co
     }
 
     // ---------------- phase 3: PS, QV of the parked levels, then the upper column ----------------
-    const float psn_f = (float)psn;
     if (active) {
         a.PS_out[c] = psn_f;
         a.dps_out[c] = (float)dps;
         for (int l = L - 1; l >= lst; --l) {
-            const float pf = (float)fma(psn, s_bkm[l], s_akm[l]);
-            const float e = st_e[(size_t)(l - lst) * NT + tid];
-            st_stream(a.QV_out + (long long)l * n + c, __fdividef(0.622f * e, pf - 0.378f * e));
+            const float2 m = s_m[l];
+            const float e = st_e[(l - lst) * NT + tid];
+            st_stream(a.QV_out + (uint32_t)l * n + c,
+                      0.622f * e * fast_rcp(fmaf(-0.378f, e, fmaf(psn_f, m.y, m.x))));
         }
     }
-    if (lst > 0) {
-        float t0[kU], q0[kU], u0[kU], v0[kU], t1[kU], q1[kU], u1[kU], v1[kU];
-        load_batch(lst - 1, 0, t0, q0, u0, v0);
-        for (int l0 = lst - 1; l0 >= 0; l0 -= kU) {
-            load_batch(l0 - kU, 0, t1, q1, u1, v1);
-#pragma unroll
-            for (int i = 0; i < kU; ++i) {
-                const int l = l0 - i;
-                if (l >= 0) {
-                    double Tp; float e_pgw;
-                    level(l, t0[i], q0[i], u0[i], v0[i], Tp, e_pgw);
-                    const float pf = (float)fma(psn, s_bkm[l], s_akm[l]);
-                    if (active)
-                        st_stream(a.QV_out + (long long)l * n + c,
-                                  __fdividef(0.622f * e_pgw, pf - 0.378f * e_pgw));
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < kU; ++i) { t0[i] = t1[i]; q0[i] = q1[i]; u0[i] = u1[i]; v0[i] = v1[i]; }
-        }
+    for (int l = lst - 1; l >= 0; --l) {
+        __pipeline_wait_prior(kRing - 1);
+        const float *slot = my_ring + (size_t)(l % (kRing + 1)) * 4 * NT;
+        const float t = slot[0], q = slot[NT], u = slot[2 * NT], v = slot[3 * NT];
+        prefetch(l - kRing);
+        float dta, e_pgw;
+        level(l, t, q, u, v, dta, e_pgw);
+        const float2 m = s_m[l];
+        if (active)
+            st_stream(a.QV_out + (uint32_t)l * n + c,
+                      0.622f * e_pgw * fast_rcp(fmaf(-0.378f, e_pgw, fmaf(psn_f, m.y, m.x))));
     }
+    __pipeline_wait_prior(0);
 
     // ---------------- bookkeeping for the host-side checks ----------------
-    float p_top = active ? fmaf(ps_f, s_bkmf[0], s_akmf[0]) : INFINITY;   // functions.py:417
+    float p_top = active ? fmaf(ps_f, s_m[0].y, s_m[0].x) : INFINITY;    // functions.py:417
     p_top = warp_min(p_top);
     min_src_p = warp_min(active ? min_src_p : INFINITY);
     if ((tid & 31) == 0) {
@@ -396,14 +455,17 @@ int stash_top(const double *ak, const double *bk, int nlev, double p_ref, double
 }
 
 size_t column_smem(int nlev, int nplev, int np, int nt) {
-    return sizeof(double) * (size_t)(2 * (nlev + 1) + 2 * nlev) +
-           (size_t)np * nt * (sizeof(double) + sizeof(float)) +
-           sizeof(float) * (size_t)(2 * nlev + nplev) + 16;
+    return sizeof(double) * 2 * (size_t)(nlev + 1) +                       // (ak, bk)
+           (size_t)np * nt * (sizeof(double) + sizeof(float)) +            // T_pgw, e_pgw stash
+           sizeof(float) * (size_t)(pgw::kRing + 1) * 4 * nt +             // cp.async ring
+           sizeof(float) * 2 * (size_t)nlev + sizeof(float) * 3 * (size_t)nplev + 16;
 }
 
 int validate(const pgw_timestep_args *a) {
     if (!a) return PGW_E_INVALID;
     if (a->ncol <= 0 || a->nlev < 2 || a->nplev < 2 || a->nplev > 64) return PGW_E_INVALID;
+    // 32-bit element offsets inside the kernel
+    if ((unsigned long long)a->ncol * (unsigned long long)(a->nlev + 1) >= (1ull << 30)) return PGW_E_INVALID;
     if (a->nsoil < 0 || a->nsoil > PGW_MAX_SOIL) return PGW_E_INVALID;
     if (a->k_spec < 1 || a->k_spec > PGW_MAX_ITER) return PGW_E_INVALID;
     const void *need[] = {a->ak_host, a->bk_host, a->ak, a->bk, a->akm, a->bkm, a->plev, a->PS, a->FIS, a->FR_LAND, a->FR_SEA_ICE,

@@ -167,18 +167,22 @@ class PGWEngine:
         self.group = group
         self.k_pred = 8
         self._ws = {}
-        self.stats = dict(timesteps=0, rewrites=0, reruns=0)
+        self.stats = dict(timesteps=0, rewrites=0, reruns=0, launches=0)
+        self.kernel_events = None       # set to [] to collect CUDA events around the column kernel
 
     # ------------------------------------------------------------------ workspace
-    def _workspace(self, ncol, max_iter):
-        key = (ncol, max_iter)
+    def _workspace(self, ncol, max_iter, slot=0):
+        """Per-slot scratch (iteration trajectory + status words).  Timesteps in flight on
+        different streams must use different slots."""
+        key = (ncol, max_iter, slot)
         ws = self._ws.get(key)
         if ws is None:
+            self._ws = {k: v for k, v in self._ws.items() if k[:2] == (ncol, max_iter)}
             ws = dict(
                 traj=torch.empty((max_iter, ncol), device=self.device, dtype=torch.float32),
                 status=torch.zeros(_STATUS_BYTES, device=self.device, dtype=torch.uint8),
             )
-            self._ws = {key: ws}
+            self._ws[key] = ws
         return ws
 
     def alloc_outputs(self, ny, nx, nsoil):
@@ -190,7 +194,7 @@ class PGWEngine:
 
     # ------------------------------------------------------------------ submit
     def submit(self, era, era_step_dt, out=None, ignore_top_pressure_error=False, k_spec=None,
-               file_name="<memory>"):
+               file_name="<memory>", slot=0):
         """
         Enqueue one timestep on the current CUDA stream.  ``era``: float32 CUDA
         tensors PS, FIS, FR_LAND, FR_SEA_ICE, T_SKIN [1,ny,nx], T_SO [1,S,ny,nx],
@@ -227,7 +231,7 @@ class PGWEngine:
         if k_spec is None:
             k_spec = self.k_pred
         k_spec = max(1, min(int(k_spec), k_max))
-        ws = self._workspace(ncol, k_max)
+        ws = self._workspace(ncol, k_max, slot)
         status = ws["status"]
 
         zg = ds.vars["zg"]
@@ -271,7 +275,14 @@ class PGWEngine:
 
         status[8 * N.PGW_MAX_ITER + 24:].zero_()                          # clear the sticky error word
         st = _stream()
+        if self.kernel_events is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         N.check(N.lib.pgw_timestep(C.byref(a), st), "pgw_timestep")
+        if self.kernel_events is not None:
+            e1.record()
+            self.kernel_events.append((e0, e1))
+        self.stats["launches"] += 4
         if self.group is not None:
             # latitude-band mode: the stopping rule is global over all bands
             import torch.distributed as dist
@@ -283,7 +294,7 @@ class PGWEngine:
         ev = torch.cuda.Event()
         ev.record()
         ctx = dict(era=era, when=era_step_dt, ignore_top=ignore_top_pressure_error, k_spec=k_spec,
-                   k_max=k_max, keep=(f, a), file_name=file_name)
+                   k_max=k_max, keep=(f, a), file_name=file_name, slot=slot)
         return Pending(self, a, out, host, ev, ctx)
 
     # ------------------------------------------------------------------ completion
@@ -309,13 +320,13 @@ class PGWEngine:
             self.ps_bound *= 1.25
             self.stats["reruns"] += 1
             return self.submit(ctx["era"], ctx["when"], out=p.out, ignore_top_pressure_error=ctx["ignore_top"],
-                               k_spec=ctx["k_spec"], file_name=ctx["file_name"]).result()
+                               k_spec=ctx["k_spec"], file_name=ctx["file_name"], slot=ctx["slot"]).result()
         if not converged:
             if ctx["k_spec"] >= ctx["k_max"]:
                 raise ValueError(MSG_NOCONV.format(ctx["file_name"]))   # step_03:315-319
             self.stats["reruns"] += 1
             return self.submit(ctx["era"], ctx["when"], out=p.out, ignore_top_pressure_error=ctx["ignore_top"],
-                               k_spec=ctx["k_max"], file_name=ctx["file_name"]).result()
+                               k_spec=ctx["k_max"], file_name=ctx["file_name"], slot=ctx["slot"]).result()
         self.k_pred = int(n_iter)
         self.stats["timesteps"] += 1
         self.stats["rewrites"] += int(rewritten)

@@ -1,0 +1,99 @@
+"""
+Work partitioning over GPUs and the reference-compatible ``IterMP`` driver.
+
+The reference parallelises over ERA5 files with a process pool (parallel.py:12-68,
+one file = one timestep = one task).  Here one process drives one B200:
+  * many timesteps: rank r takes timesteps r, r+W, ... (``timesteps_for_rank``);
+    the only collective is one NCCL broadcast of the delta climatology
+    (``broadcast_deltas``);
+  * a single snapshot: contiguous latitude bands (``split_rows``); the
+    field-global stopping rule of the ps iteration then needs a MAX all-reduce of
+    the per-iteration error vector (done inside ``PGWEngine.submit`` when the
+    engine is given a process group).
+``IterMP`` keeps the reference's call signature; tasks run in this process on
+the current GPU (njobs == 1) or in ``njobs`` spawned workers, worker i bound to
+GPU i % device_count.
+"""
+import multiprocessing as mp
+import os
+
+
+def split_rows(ny, world):
+    """Contiguous latitude bands: the first ``world-1`` ranks get ny // world rows,
+    the last one the remainder (721 rows on 8 ranks -> 7 x 90 + 91)."""
+    base = ny // world
+    bounds = []
+    for r in range(world):
+        start = r * base
+        stop = ny if r == world - 1 else (r + 1) * base
+        bounds.append((start, stop))
+    return bounds
+
+
+def timesteps_for_rank(n_steps, rank, world):
+    """Round-robin assignment of independent timesteps to ranks."""
+    return list(range(rank, n_steps, world))
+
+
+def decide_n_iter(maxerr, thresh):
+    """First iteration count N with max|phi error| <= thresh (step_03_apply_to_era.py:189,308),
+    or 0 if none of the recorded iterations converged.  Host mirror of the device-side scan,
+    used on the merged (all-reduced) error vector."""
+    for k, e in enumerate(maxerr):
+        if not (e > thresh):
+            return k + 1
+    return 0
+
+
+def broadcast_deltas(deltas, src=0, group=None):
+    """NCCL-broadcast every tensor of a ``DeltaSet`` from ``src``; returns elapsed ms."""
+    import torch
+    import torch.distributed as dist
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for t in deltas.tensors():
+        dist.broadcast(t, src=src, group=group)
+    e1.record()
+    torch.cuda.synchronize()
+    deltas.refresh_derived()
+    return e0.elapsed_time(e1)
+
+
+def _worker(payload):
+    func, kwargs, worker_slot = payload
+    try:
+        import torch
+        if torch.cuda.is_available():
+            torch.cuda.set_device(worker_slot % torch.cuda.device_count())
+    except ImportError:
+        pass
+    return func(**kwargs)
+
+
+class IterMP:
+    """Same interface as the reference's ``IterMP`` (parallel.py:36-68):
+    ``IterMP(njobs, run_async).run(func, fargs, step_args)`` then ``.output``."""
+
+    def __init__(self, njobs=None, run_async=False):
+        self.run_async = run_async
+        self.njobs = 1 if njobs is None else int(njobs)
+        print('IterMP: njobs = ' + str(self.njobs))
+        self.output = None
+
+    def run(self, func, fargs={}, step_args=None):
+        tasks = []
+        for i in range(len(step_args)):
+            kw = dict(fargs)
+            kw.update(step_args[i])
+            tasks.append(kw)
+        if self.njobs > 1:
+            ctx = mp.get_context("spawn")
+            with ctx.Pool(processes=self.njobs) as pool:
+                payload = [(func, kw, i % self.njobs) for i, kw in enumerate(tasks)]
+                if self.run_async:
+                    self.output = pool.map_async(_worker, payload).get()
+                else:
+                    self.output = pool.map(_worker, payload)
+        else:
+            self.output = [func(**kw) for kw in tasks]

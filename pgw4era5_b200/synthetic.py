@@ -83,14 +83,16 @@ def _esat(ta):
     return alpha * ew + (1 - alpha) * ei
 
 
-def make_era5(ny, nx, seed, device="cpu", nlev=137, lat=None, lon=None):
+def make_era5(ny, nx, seed, device="cpu", nlev=137, lat=None, lon=None, orog_seed=None):
     """
     One synthetic ERA5 timestep on an (ny, nx) grid.  Returns a dict of float32
     torch tensors (plus float64 numpy ``ak``/``bk``/``soil1``/``lat``/``lon``).
+    ``orog_seed`` (default: ``seed``) seeds orography, surface pressure and the
+    land mask, so several timesteps over the same terrain can be generated.
     """
     dev = torch.device(device)
     gen = torch.Generator(device=dev)
-    gen.manual_seed(int(seed))
+    gen.manual_seed(int(seed if orog_seed is None else orog_seed))
     if lat is None:
         lat = np.linspace(-90.0, 90.0, ny) if ny > 1 else np.zeros(1)
     if lon is None:
@@ -107,6 +109,10 @@ def make_era5(ny, nx, seed, device="cpu", nlev=137, lat=None, lon=None):
     ps = 101325.0 * torch.exp(-CON_G * zs.to(f64) / (CON_RD * 270.0))
     ps = ps * (1.0 + 0.01 * _smooth_noise(gen, ny, nx, 10, dev).to(f64))
     PS = ps.to(torch.float32)
+    if orog_seed is not None:
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(int(seed))
+        PS = (ps * (1.0 + 0.004 * _smooth_noise(gen, ny, nx, 10, dev).to(f64))).to(torch.float32)
 
     tsfc = 288.0 - 0.0065 * zs + 8.0 * _smooth_noise(gen, ny, nx, 16, dev)
     lat_t = torch.as_tensor(lat, device=dev, dtype=torch.float32).reshape(ny, 1)
