@@ -53,19 +53,25 @@ __device__ __forceinline__ double rcp64_approx(double x) {
     return r;
 }
 
-// ln(pb/pt), pb >= pt > 0, float64 accuracy ~1e-13 relative for s < 0.06 (all
-// adjacent ERA5 half levels below ~100 hPa): 2 atanh(s), s = (pb-pt)/(pb+pt).
-__device__ __forceinline__ double ln_ratio(double pb, double pt) {
+// ln(pb/pt), pb >= pt > 0, in float64 without a float64 log or divide:
+// 2 atanh(s), s = (pb-pt)/(pb+pt) = 2 s (1 + s^2/3 + s^4/5 + s^6/7 + ...).
+// Truncated after s^6/7 the relative error is s^8/9 < 2e-11 for s < 0.06, far below
+// the 1e-9 the ps iteration needs; all adjacent ERA5 half levels below ~100 hPa
+// have s < 0.05.  FAST = the host has verified s < 0.06 for every layer the
+// iteration can touch, so the exact-log branch is compiled out.
+struct LnConst { double c3, c5, c7; };
+
+template <bool FAST>
+__device__ __forceinline__ double ln_ratio(double pb, double pt, const LnConst &k) {
     const double d = pb - pt;
     const double sm = pb + pt;
     double r = rcp64_approx(sm);
-    r = fma(r, fma(-sm, r, 1.0), r);            // one Newton step: ~1e-12
+    r = fma(r, fma(-sm, r, 1.0), r);            // one Newton step: ~1e-12 relative
     const double s = d * r;
-    if (s > 0.06) return log(pb / pt);          // coarse layers: exact path
+    if (!FAST) { if (s > 0.06) return log(pb / pt); }
     const double s2 = s * s;
-    double poly = fma(s2, 2.0 / 9.0, 2.0 / 7.0);
-    poly = fma(s2, poly, 2.0 / 5.0);
-    poly = fma(s2, poly, 2.0 / 3.0);
+    double poly = fma(s2, k.c7, k.c5);
+    poly = fma(s2, poly, k.c3);
     poly = fma(s2, poly, 2.0);
     return s * poly;
 }
@@ -75,25 +81,20 @@ __device__ __forceinline__ double ln_ratio(double pb, double pt) {
 // State: lo node (index, pressure, values) and the differences to the hi node.
 // inv_w == 0 encodes "no interpolation": at/after the last node, or (after the
 // walk has passed node 0) before the first node; then the lo values are returned.
+// The node below lo is prefetched as raw (lo, hi) time slabs and blended when used.
 struct Walk2 {
     int lo;                 // index of the lo node; -1 once the target is above node 0
     float p_lo, inv_p_lo, inv_w;
-    float a_lo, a_d, a_nx;  // value at lo, (hi - lo), prefetched value of node lo-1
-    float b_lo, b_d, b_nx;
+    float a_lo, a_d, b_lo, b_d;
+    float a_n0, a_n1, b_n0, b_n1;
 };
 
 struct Tslab32 { const float *lo, *hi; float w; };
 
-__device__ __forceinline__ float node_value(const Tslab32 &s, uint32_t off) {
-    const float lo = __ldg(s.lo + off);
-    if (s.w == 0.0f) return lo;
-    return fmaf(s.w, __ldg(s.hi + off) - lo, lo);
-}
-
 constexpr int kRing = 6;     // levels in flight per thread (cp.async ring, +1 spare slot)
 
-template <int NT>
-__global__ void __launch_bounds__(NT)
+template <int NT, bool FAST>
+__global__ void __launch_bounds__(NT, 2)
 pgw_column_kernel(const __grid_constant__ pgw_timestep_args a, const int lst, const int np) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int L = a.nlev, K = a.nplev;
@@ -124,25 +125,33 @@ pgw_column_kernel(const __grid_constant__ pgw_timestep_args a, const int lst, co
 
     const uint32_t n = (uint32_t)a.ncol;
     uint32_t c = blockIdx.x * NT + tid;
-    const bool active = c < n;
-    if (!active) c = n - 1;          // compute redundantly, never store
+    // Threads past the last column mirror column n-1: they compute and store exactly the
+    // same values to the same addresses, which keeps the whole kernel free of tail branches.
+    if (c >= n) c = n - 1;
     unsigned errbits = 0;
 
     // ---- async ring: this thread's T, QV, U, V of one level per slot
-    float *my_ring = ring + tid;
-    auto prefetch = [&](int l) {
-        if (l >= 0) {
-            float *dst = my_ring + (size_t)(l % (kRing + 1)) * 4 * NT;
-            const uint32_t off = (uint32_t)l * n + c;
-            __pipeline_memcpy_async(dst, a.T + off, 4);
-            __pipeline_memcpy_async(dst + NT, a.QV + off, 4);
-            __pipeline_memcpy_async(dst + 2 * NT, a.U + off, 4);
-            __pipeline_memcpy_async(dst + 3 * NT, a.V + off, 4);
+    const float *gT = a.T, *gQ = a.QV, *gU = a.U, *gV = a.V;
+    float *oT = a.T_out, *oQ = a.QV_out, *oU = a.U_out, *oV = a.V_out;
+    float *const my_ring = ring + tid;
+    int slot_w = 0;                                  // slot the next prefetch writes
+    uint32_t off_w = (uint32_t)(L - 1) * n + c;      // element offset of the next prefetched level
+    int lev_w = L - 1;
+    auto prefetch = [&]() {
+        if (lev_w >= 0) {
+            float *dst = my_ring + slot_w * (4 * NT);
+            __pipeline_memcpy_async(dst, gT + off_w, 4);
+            __pipeline_memcpy_async(dst + NT, gQ + off_w, 4);
+            __pipeline_memcpy_async(dst + 2 * NT, gU + off_w, 4);
+            __pipeline_memcpy_async(dst + 3 * NT, gV + off_w, 4);
         }
         __pipeline_commit();
+        --lev_w; off_w -= n;
+        slot_w = (slot_w == kRing) ? 0 : slot_w + 1;
     };
 #pragma unroll
-    for (int i = 0; i < kRing; ++i) prefetch(L - 1 - i);
+    for (int i = 0; i < kRing; ++i) prefetch();
+    int slot_r = 0;                                  // slot the next level is read from
 
     // ---------------- surface, skin and soil (step_03:103-146) ----------------
     const float ps_f = __ldg(a.PS + c);
@@ -160,13 +169,11 @@ pgw_column_kernel(const __grid_constant__ pgw_timestep_args a, const int lst, co
             comb = (double)fr * dts + (double)(1.0f - fr) * dtos;
         }
         const double clim = (double)__ldg(a.ts_clim + c);
-        if (active) {
-            a.FR_SEA_ICE_out[c] = sic;
-            a.T_SKIN_out[c] = (float)((double)__ldg(a.T_SKIN + c) + comb);
-            for (int s = 0; s < a.nsoil; ++s) {
-                const double dso = clim + a.soil_decay[s] * (comb - clim);
-                a.T_SO_out[(uint32_t)s * n + c] = (float)((double)__ldg(a.T_SO + (uint32_t)s * n + c) + dso);
-            }
+        a.FR_SEA_ICE_out[c] = sic;
+        a.T_SKIN_out[c] = (float)((double)__ldg(a.T_SKIN + c) + comb);
+        for (int s = 0; s < a.nsoil; ++s) {
+            const double dso = clim + a.soil_decay[s] * (comb - clim);
+            a.T_SO_out[(uint32_t)s * n + c] = (float)((double)__ldg(a.T_SO + (uint32_t)s * n + c) + dso);
         }
     }
 
@@ -174,9 +181,14 @@ pgw_column_kernel(const __grid_constant__ pgw_timestep_args a, const int lst, co
     const auto tw = [](const pgw_tslab &s) { return (s.x_new == 0.0) ? 0.0f : (float)(s.x_new / s.x_hi); };
     const Tslab32 v_ta{a.ta.lo, a.ta.hi, tw(a.ta)}, v_hur{a.hur.lo, a.hur.hi, tw(a.hur)};
     const Tslab32 v_ua{a.ua.lo, a.ua.hi, tw(a.ua)}, v_va{a.va.lo, a.va.hi, tw(a.va)};
-    const auto node_off = [&](int j) -> uint32_t {
-        return (uint32_t)(a.plev_descending ? (K - 1 - j) : j) * n + c;
+    const int desc = a.plev_descending;
+    // raw loads of node j of a variable pair (time slabs lo/hi); blended when consumed
+    auto load_raw = [&](const Tslab32 &va, const Tslab32 &vb, int j, float &a0, float &a1, float &b0, float &b1) {
+        const uint32_t off = (uint32_t)(desc ? (K - 1 - j) : j) * n + c;
+        a0 = __ldg(va.lo + off); a1 = __ldg(va.hi + off);
+        b0 = __ldg(vb.lo + off); b1 = __ldg(vb.hi + off);
     };
+    auto blend = [](float w, float x0, float x1) { return (w == 0.0f) ? x0 : fmaf(w, x1 - x0, x0); };
 
     Walk2 wA, wB;
     {
@@ -193,48 +205,56 @@ pgw_column_kernel(const __grid_constant__ pgw_timestep_args a, const int lst, co
         wA.lo = s; wA.p_lo = psh; wA.inv_p_lo = fast_rcp(psh); wA.inv_w = 0.0f;
         wA.a_lo = (float)blend_f64(a.tas, c); wA.a_d = 0.0f;
         wA.b_lo = (float)blend_f64(a.hurs, c); wA.b_d = 0.0f;
-        wA.a_nx = wA.a_lo; wA.b_nx = wA.b_lo;
-        if (s >= 1) { wA.a_nx = node_value(v_ta, node_off(s - 1)); wA.b_nx = node_value(v_hur, node_off(s - 1)); }
+        wA.a_n0 = wA.a_n1 = wA.b_n0 = wA.b_n1 = 0.0f;
+        if (s >= 1) load_raw(v_ta, v_hur, s - 1, wA.a_n0, wA.a_n1, wA.b_n0, wA.b_n1);
 
+        float x0, x1, y0, y1;
+        load_raw(v_ua, v_va, K - 1, x0, x1, y0, y1);
         wB.lo = K - 1; wB.p_lo = s_plev[K - 1]; wB.inv_p_lo = s_inv_plev[K - 1]; wB.inv_w = 0.0f;
-        wB.a_lo = node_value(v_ua, node_off(K - 1)); wB.a_d = 0.0f;
-        wB.b_lo = node_value(v_va, node_off(K - 1)); wB.b_d = 0.0f;
-        wB.a_nx = node_value(v_ua, node_off(K - 2)); wB.b_nx = node_value(v_va, node_off(K - 2));
+        wB.a_lo = blend(v_ua.w, x0, x1); wB.a_d = 0.0f;
+        wB.b_lo = blend(v_va.w, y0, y1); wB.b_d = 0.0f;
+        load_raw(v_ua, v_va, K - 2, wB.a_n0, wB.a_n1, wB.b_n0, wB.b_n1);
     }
     float min_src_p = (wA.lo == 0) ? wA.p_lo : s_plev[0];
 
     // advance a walker until p_lo <= p (or the first node has been passed)
-    auto advance = [&](Walk2 &w, float p, const Tslab32 &va, const Tslab32 &vb, bool synth_top) {
-        while (w.lo >= 0 && w.p_lo > p) {
+    auto advance = [&](Walk2 &w, float p, const Tslab32 &va, const Tslab32 &vb) {
+        while (w.p_lo > p) {
             const float hi_p = w.p_lo, hi_a = w.a_lo, hi_b = w.b_lo;
-            const bool from_synth = synth_top && (hi_p != s_plev[w.lo]);   // leaving the (ps_hist, sfc) node
+            const bool from_synth = (hi_p != s_plev[w.lo]);     // leaving the (ps_hist, sfc) node
             --w.lo;
             if (w.lo >= 0) {
                 w.p_lo = s_plev[w.lo]; w.inv_p_lo = s_inv_plev[w.lo];
-                w.a_lo = w.a_nx; w.b_lo = w.b_nx;
+                w.a_lo = blend(va.w, w.a_n0, w.a_n1); w.b_lo = blend(vb.w, w.b_n0, w.b_n1);
                 w.a_d = hi_a - w.a_lo; w.b_d = hi_b - w.b_lo;
                 w.inv_w = from_synth ? fast_rcp(fast_lg2(hi_p * w.inv_p_lo)) : s_inv_w[w.lo];
-                if (w.lo >= 1) { w.a_nx = node_value(va, node_off(w.lo - 1)); w.b_nx = node_value(vb, node_off(w.lo - 1)); }
+                if (w.lo >= 1) load_raw(va, vb, w.lo - 1, w.a_n0, w.a_n1, w.b_n0, w.b_n1);
             } else {
-                // above node 0: constant extrapolation with node 0's values (they are in hi_*)
-                w.a_lo = hi_a; w.b_lo = hi_b; w.a_d = 0.0f; w.b_d = 0.0f; w.inv_w = 0.0f;
+                // above node 0: constant extrapolation with node 0's values; p_lo = 0 ends the walk
+                w.a_d = 0.0f; w.b_d = 0.0f; w.inv_w = 0.0f; w.p_lo = 0.0f; w.inv_p_lo = 1.0f;
             }
         }
     };
 
+    LnConst lk{2.0 / 3.0, 2.0 / 5.0, 2.0 / 7.0};
+    asm volatile("" : "+d"(lk.c3), "+d"(lk.c5), "+d"(lk.c7));     // keep the constants in registers
+
     const double pref = a.p_ref;
-    double pb_era = fma(PSd, s_hl[L].y, s_hl[L].x);
+    const double2 hl_sfc = s_hl[L];
+    double pb_era = fma(PSd, hl_sfc.y, hl_sfc.x);
     double acc_era = 0.0;
-    if (pb_era < pref) errbits |= PGW_ERR_PREF_BELOW_SFC;
-    float psn_f = ps_f;                  // ps used for QV; replaced after the iteration
+    bool era_open = pb_era >= pref;                 // still below p_ref
+    if (!era_open) errbits |= PGW_ERR_PREF_BELOW_SFC;
+    float psn_f = ps_f;                             // ps used for QV; replaced after the iteration
 
     // One model level: deltas at p, RH of the ERA state, PGW state, outputs T/U/V.
-    // Returns tm273 + dta pieces through Tp (float64 T_pgw) and e_pgw.
-    auto level = [&](int l, float t, float q, float u, float v, float &dta_out, float &e_pgw) {
+    auto level = [&](int l, uint32_t off, float t, float q, float u, float v, float &dta_out, float &e_pgw) {
         const float2 m = s_m[l];
         const float p = fmaf(ps_f, m.y, m.x);
-        if (wA.p_lo > p) advance(wA, p, v_ta, v_hur, true);
-        if (wB.p_lo > p) advance(wB, p, v_ua, v_va, false);
+        if (fmaxf(wA.p_lo, wB.p_lo) > p) {
+            advance(wA, p, v_ta, v_hur);
+            advance(wB, p, v_ua, v_va);
+        }
         const float l2b = fast_lg2(p * wB.inv_p_lo);
         const float l2a = (wA.inv_p_lo == wB.inv_p_lo) ? l2b : fast_lg2(p * wA.inv_p_lo);
         const float tA = l2a * wA.inv_w, tB = l2b * wB.inv_w;
@@ -256,92 +276,107 @@ pgw_column_kernel(const __grid_constant__ pgw_timestep_args a, const int lst, co
         const float rr = fast_rcp(de * dp);                   // one reciprocal for both states
         float es_e = 611.21f * fast_ex2(ae * dTe * (rr * dp));
         float es_p = 611.21f * fast_ex2(ap * dTp * (rr * de));
-        if (!(dTe >= 0.0f || dTe <= -23.0f)) {                // mixed phase (or NaN): blend water/ice
-            const float ew = 611.21f * __expf(__fdividef(17.502f * dTe, tm273 + (273.0f - 32.19f)));
-            const float r = (dTe + 23.0f) * (1.0f / 23.0f), al = r * r;
-            es_e = al * ew + (1.0f - al) * es_e;
-        }
-        if (!(dTp >= 0.0f || dTp <= -23.0f)) {
-            const float ew = 611.21f * __expf(__fdividef(17.502f * dTp, tkp + (273.0f - 32.19f)));
-            const float r = (dTp + 23.0f) * (1.0f / 23.0f), al = r * r;
-            es_p = al * ew + (1.0f - al) * es_p;
+        const bool mix_e = !(dTe >= 0.0f || dTe <= -23.0f), mix_p = !(dTp >= 0.0f || dTp <= -23.0f);
+        if (mix_e || mix_p) {                                 // mixed phase (or NaN): blend water/ice
+            if (mix_e) {
+                const float ew = 611.21f * __expf(__fdividef(17.502f * dTe, tm273 + (273.0f - 32.19f)));
+                const float r = (dTe + 23.0f) * (1.0f / 23.0f), al = r * r;
+                es_e = al * ew + (1.0f - al) * es_e;
+            }
+            if (mix_p) {
+                const float ew = 611.21f * __expf(__fdividef(17.502f * dTp, tkp + (273.0f - 32.19f)));
+                const float r = (dTp + 23.0f) * (1.0f / 23.0f), al = r * r;
+                es_p = al * ew + (1.0f - al) * es_p;
+            }
         }
         // RELHUM of the ERA state (functions.py:107-116) + delta, back to vapour pressure (:123)
         const float rh_pgw = fmaf(100.0f * q * p, fast_rcp((0.622f + 0.378f * q) * es_e), dhur);
         e_pgw = rh_pgw * 0.01f * es_p;
         dta_out = dta;
-        if (active) {
-            const uint32_t off = (uint32_t)l * n + c;
-            st_stream(a.T_out + off, t + dta);     // == (float)((double)t + (double)dta)
-            st_stream(a.U_out + off, u + dua);
-            st_stream(a.V_out + off, v + dva);
-        }
+        st_stream(oT + off, t + dta);     // == (float)((double)t + (double)dta)
+        st_stream(oU + off, u + dua);
+        st_stream(oV + off, v + dva);
     };
 
     // ---------------- phase 1: surface .. p_ref, parked in shared memory ----------------
-    for (int l = L - 1; l >= lst; --l) {
-        __pipeline_wait_prior(kRing - 1);
-        const float *slot = my_ring + (size_t)(l % (kRing + 1)) * 4 * NT;
-        const float t = slot[0], q = slot[NT], u = slot[2 * NT], v = slot[3 * NT];
-        prefetch(l - kRing);
-        float dta, e_pgw;
-        level(l, t, q, u, v, dta, e_pgw);
-        st_T[(l - lst) * NT + tid] = (double)t + (double)dta;
-        st_e[(l - lst) * NT + tid] = e_pgw;
-        // geopotential of the ERA state (functions.py:128-189)
-        const double2 hl = s_hl[l];
-        const double pt = fma(PSd, hl.y, hl.x);
-        if (pb_era >= pref) {
-            const double tv = (double)t * (1.0 + 0.61 * (double)q);
-            acc_era = fma(tv, ln_ratio(pb_era, pt > pref ? pt : pref), acc_era);
+    uint32_t off = (uint32_t)(L - 1) * n + c;
+    {
+        double *pT = st_T + (size_t)(L - 1 - lst) * NT + tid;
+        float *pe = st_e + (size_t)(L - 1 - lst) * NT + tid;
+        for (int l = L - 1; l >= lst; --l, off -= n, pT -= NT, pe -= NT) {
+            __pipeline_wait_prior(kRing - 1);
+            const float *slot = my_ring + slot_r * (4 * NT);
+            const float t = slot[0], q = slot[NT], u = slot[2 * NT], v = slot[3 * NT];
+            slot_r = (slot_r == kRing) ? 0 : slot_r + 1;
+            prefetch();
+            float dta, e_pgw;
+            level(l, off, t, q, u, v, dta, e_pgw);
+            const double td = (double)t;
+            *pT = td + (double)dta;
+            *pe = e_pgw;
+            // geopotential of the ERA state (functions.py:128-189)
+            if (era_open) {
+                const double2 hl = s_hl[l];
+                double pt = fma(PSd, hl.y, hl.x);
+                if (pt < pref) { pt = pref; era_open = false; }     // layer that contains p_ref (:174-179)
+                const double tv = fma(td, 0.61 * (double)q, td);
+                acc_era = fma(tv, ln_ratio<FAST>(pb_era, pt, lk), acc_era);
+                pb_era = pt;
+            }
         }
-        pb_era = pt;
     }
     const double fis = (double)__ldg(a.FIS + c);
     const double phi_era = fis + kRd * acc_era;
     const double gdzg = blend_f64(a.zg_ref, c) * kG;              // step_03:292-295
-    const double t_low = st_T[(L - 1 - lst) * NT + tid];         // ta_pgw on the lowest level
-    const double2 hl_sfc = s_hl[L];
+    const double *const bT = st_T + (size_t)(L - 1 - lst) * NT + tid;   // lowest level of the stash
+    const float *const be = st_e + (size_t)(L - 1 - lst) * NT + tid;
+    const double t_low = *bT;                                     // ta_pgw on the lowest level
 
     // ---------------- phase 2: surface-pressure fixed point (step_03:182-319) ----------------
     // The loads of the upper column are already in flight and overlap this phase.
     double dps = 0.0, adj = 0.0, psn = PSd;
-    for (int k = 0; k < a.k_spec; ++k) {
+    int ltop = lst + 1;                 // first layer (from the top) lying entirely below p_ref
+    float *traj = a.dps_traj + c;
+    for (int k = 0; k < a.k_spec; ++k, traj += n) {
         dps += adj;
         psn = PSd + dps;
         psn_f = (float)psn;
-        if (active) a.dps_traj[(uint32_t)k * n + c] = (float)dps;
+        *traj = (float)dps;
         if (psn > a.ps_bound) errbits |= PGW_ERR_PS_BOUND;
         double pb = fma(psn, hl_sfc.y, hl_sfc.x);
         if (pb < pref) errbits |= PGW_ERR_PREF_BELOW_SFC;
+        // layers ltop..L-1 are entirely below p_ref for this ps; it moves by at most a level or two
+        while (ltop > lst) { const double2 h = s_hl[ltop - 1]; if (fma(psn, h.y, h.x) >= pref) --ltop; else break; }
+        while (ltop < L) { const double2 h = s_hl[ltop]; if (fma(psn, h.y, h.x) < pref) ++ltop; else break; }
         double acc = 0.0;
+        const double *pT = bT;
+        const float *pe = be;
         int l = L - 1;
-#pragma unroll 4
-        for (; l >= lst; --l) {
+#pragma unroll 2
+        for (; l >= ltop; --l, pT -= NT, pe -= NT) {
             const double2 hl = s_hl[l];
-            const double pt = fma(psn, hl.y, hl.x);
-            if (pt < pref) break;                                  // partial layer below
             const float2 m = s_m[l];
-            const float e = st_e[(l - lst) * NT + tid];
-            const double Td = st_T[(l - lst) * NT + tid];
+            const float e = *pe;
+            const double Td = *pT;
+            const double pt = fma(psn, hl.y, hl.x);
             // Tv = T (1 + 0.61 hus), hus = 0.622 e / (p - 0.378 e)   (functions.py:66-72, :144)
             const float g = fast_rcp(fmaf(-0.378f, e, fmaf(psn_f, m.y, m.x)));
             const double tv = fma(Td, (double)((0.61f * 0.622f) * e * g), Td);
-            acc = fma(tv, ln_ratio(pb, pt), acc);
+            acc = fma(tv, ln_ratio<FAST>(pb, pt, lk), acc);
             pb = pt;
         }
         if (l >= lst && pb >= pref) {                              // layer that contains p_ref (:174-179)
             const float2 m = s_m[l];
-            const float e = st_e[(l - lst) * NT + tid];
-            const double Td = st_T[(l - lst) * NT + tid];
+            const float e = *pe;
+            const double Td = *pT;
             const float g = fast_rcp(fmaf(-0.378f, e, fmaf(psn_f, m.y, m.x)));
             const double tv = fma(Td, (double)((0.61f * 0.622f) * e * g), Td);
-            acc = fma(tv, ln_ratio(pb, pref), acc);
+            acc = fma(tv, ln_ratio<FAST>(pb, pref, lk), acc);
         }
         const double phi_pgw = fis + kRd * acc;
         const double err = (phi_pgw - phi_era) - gdzg;
         adj = -a.adj_factor * psn / (kRd * t_low) * err;
-        double ae = (active && !isnan(err)) ? fabs(err) : 0.0;     // max skips NaN (step_03:308)
+        double ae = isnan(err) ? 0.0 : fabs(err);                  // max skips NaN (step_03:308)
         ae = warp_max(ae);
         if ((tid & 31) == 0 && ae > 0.0)
             atomicMax(reinterpret_cast<unsigned long long *>(a.maxerr + k),
@@ -349,39 +384,38 @@ pgw_column_kernel(const __grid_constant__ pgw_timestep_args a, const int lst, co
     }
 
     // ---------------- phase 3: PS, QV of the parked levels, then the upper column ----------------
-    if (active) {
-        a.PS_out[c] = psn_f;
-        a.dps_out[c] = (float)dps;
-        for (int l = L - 1; l >= lst; --l) {
+    a.PS_out[c] = psn_f;
+    a.dps_out[c] = (float)dps;
+    {
+        const float *pe = be;
+        uint32_t o2 = (uint32_t)(L - 1) * n + c;
+        for (int l = L - 1; l >= lst; --l, pe -= NT, o2 -= n) {
             const float2 m = s_m[l];
-            const float e = st_e[(l - lst) * NT + tid];
-            st_stream(a.QV_out + (uint32_t)l * n + c,
-                      0.622f * e * fast_rcp(fmaf(-0.378f, e, fmaf(psn_f, m.y, m.x))));
+            const float e = *pe;
+            st_stream(oQ + o2, 0.622f * e * fast_rcp(fmaf(-0.378f, e, fmaf(psn_f, m.y, m.x))));
         }
     }
-    for (int l = lst - 1; l >= 0; --l) {
+    for (int l = lst - 1; l >= 0; --l, off -= n) {
         __pipeline_wait_prior(kRing - 1);
-        const float *slot = my_ring + (size_t)(l % (kRing + 1)) * 4 * NT;
+        const float *slot = my_ring + slot_r * (4 * NT);
         const float t = slot[0], q = slot[NT], u = slot[2 * NT], v = slot[3 * NT];
-        prefetch(l - kRing);
+        slot_r = (slot_r == kRing) ? 0 : slot_r + 1;
+        prefetch();
         float dta, e_pgw;
-        level(l, t, q, u, v, dta, e_pgw);
+        level(l, off, t, q, u, v, dta, e_pgw);
         const float2 m = s_m[l];
-        if (active)
-            st_stream(a.QV_out + (uint32_t)l * n + c,
-                      0.622f * e_pgw * fast_rcp(fmaf(-0.378f, e_pgw, fmaf(psn_f, m.y, m.x))));
+        st_stream(oQ + off, 0.622f * e_pgw * fast_rcp(fmaf(-0.378f, e_pgw, fmaf(psn_f, m.y, m.x))));
     }
     __pipeline_wait_prior(0);
 
     // ---------------- bookkeeping for the host-side checks ----------------
-    float p_top = active ? fmaf(ps_f, s_m[0].y, s_m[0].x) : INFINITY;    // functions.py:417
+    float p_top = fmaf(ps_f, s_m[0].y, s_m[0].x);                        // functions.py:417
     p_top = warp_min(p_top);
-    min_src_p = warp_min(active ? min_src_p : INFINITY);
+    min_src_p = warp_min(min_src_p);
     if ((tid & 31) == 0) {
         atomicMin(reinterpret_cast<unsigned *>(a.stats), __float_as_uint(fmaxf(p_top, 0.0f)));
         atomicMin(reinterpret_cast<unsigned *>(a.stats) + 1, __float_as_uint(fmaxf(min_src_p, 0.0f)));
     }
-    if (!active) errbits = 0;
     if (errbits) atomicOr(a.err, errbits);
 }
 
@@ -498,9 +532,18 @@ int pgw_timestep(const pgw_timestep_args *a, void *stream) {
     const int lst = stash_top(a->ak_host, a->bk_host, a->nlev, a->p_ref, a->ps_bound);
     const int np = a->nlev - lst;
     const size_t smem = column_smem(a->nlev, a->nplev, np, kColumnThreads);
-    auto kern = pgw::pgw_column_kernel<kColumnThreads>;
-    static thread_local size_t configured = 0;
-    if (smem > configured) {
+    // FAST: every layer the iteration can touch has s = (pb-pt)/(pb+pt) < 0.06 for all ps in
+    // [p_ref, ps_bound] (s is monotone in ps), so the series needs no exact-log fallback.
+    bool fast = true;
+    for (int l = lst; l < a->nlev; ++l)
+        for (double ps : {a->p_ref, a->ps_bound}) {
+            const double pt = a->ak_host[l] + ps * a->bk_host[l], pb = a->ak_host[l + 1] + ps * a->bk_host[l + 1];
+            if (!(pt > 0.0) || !((pb - pt) / (pb + pt) < 0.055)) fast = false;
+        }
+    auto kern = fast ? pgw::pgw_column_kernel<kColumnThreads, true> : pgw::pgw_column_kernel<kColumnThreads, false>;
+    static thread_local size_t configured[2] = {0, 0};
+    size_t &conf = configured[fast ? 1 : 0];
+    if (smem > conf) {
         int dev = 0, max_optin = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
@@ -513,7 +556,7 @@ int pgw_timestep(const pgw_timestep_args *a, void *stream) {
             return pgw_check_launch("cudaFuncSetAttribute");
         cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
                              cudaSharedmemCarveoutMaxShared);
-        configured = smem;
+        conf = smem;
     }
     pgw::pgw_timestep_init_kernel<<<1, 64, 0, st>>>(a->maxerr, a->stats);
     const unsigned grid = (unsigned)((a->ncol + kColumnThreads - 1) / kColumnThreads);
