@@ -91,18 +91,17 @@ struct Walk2 {
 
 struct Tslab32 { const float *lo, *hi; float w; };
 
-constexpr int kRing = 6;     // levels in flight per thread (cp.async ring, +1 spare slot)
+constexpr int kRing = 5;     // levels in flight per thread (cp.async ring, +1 spare slot)
 
 template <int NT, bool FAST>
-__global__ void __launch_bounds__(NT, 2)
+__global__ void __launch_bounds__(NT, 3)
 pgw_column_kernel(const __grid_constant__ pgw_timestep_args a, const int lst, const int np) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int L = a.nlev, K = a.nplev;
     // ---- shared memory carve-up
     double2 *s_hl = reinterpret_cast<double2 *>(smem);                  // [L+1] (ak, bk)
-    double *st_T = reinterpret_cast<double *>(s_hl + (L + 1));          // [np][NT] T_pgw
-    float *st_e = reinterpret_cast<float *>(st_T + (size_t)np * NT);   // [np][NT] e_pgw
-    float *ring = st_e + (size_t)np * NT;                              // [kRing+1][4][NT]
+    float2 *st_Te = reinterpret_cast<float2 *>(s_hl + (L + 1));         // [np][NT] (T_pgw rounded to fp32, e_pgw)
+    float *ring = reinterpret_cast<float *>(st_Te + (size_t)np * NT);   // [kRing+1][4][NT]
     float2 *s_m = reinterpret_cast<float2 *>(ring + (size_t)(kRing + 1) * 4 * NT);   // [L] (akm, bkm)
     float *s_plev = reinterpret_cast<float *>(s_m + L);                 // [K] ascending
     float *s_inv_plev = s_plev + K;                                     // [K]
@@ -268,22 +267,28 @@ pgw_column_kernel(const __grid_constant__ pgw_timestep_args a, const int lst, co
         // T - 273.16 is formed from the exact T - 273 so that T_pgw is never rounded to fp32
         const float tm273 = t - 273.0f;
         const float dTe = tm273 - 0.16f, tkp = tm273 + dta, dTp = tm273 + (dta - 0.16f);
-        const bool we = dTe >= 0.0f, wp = dTp >= 0.0f;
-        const float ce = we ? (273.0f - 32.19f) : (273.0f + 0.7f), cp = wp ? (273.0f - 32.19f) : (273.0f + 0.7f);
-        const float ae = we ? (17.502f * 1.4426950408889634f) : (22.587f * 1.4426950408889634f);
-        const float ap = wp ? (17.502f * 1.4426950408889634f) : (22.587f * 1.4426950408889634f);
-        const float de = tm273 + ce, dp = tkp + cp;
-        const float rr = fast_rcp(de * dp);                   // one reciprocal for both states
-        float es_e = 611.21f * fast_ex2(ae * dTe * (rr * dp));
-        float es_p = 611.21f * fast_ex2(ap * dTp * (rr * de));
-        const bool mix_e = !(dTe >= 0.0f || dTe <= -23.0f), mix_p = !(dTp >= 0.0f || dTp <= -23.0f);
-        if (mix_e || mix_p) {                                 // mixed phase (or NaN): blend water/ice
-            if (mix_e) {
+        float es_e, es_p;
+        if (fmaxf(dTe, dTp) <= -23.0f) {
+            // both states at or below 250.16 K (most of the column): ice only, alpha == 0 exactly
+            const float de = tm273 + (273.0f + 0.7f), dp = tkp + (273.0f + 0.7f);
+            const float rr = fast_rcp(de * dp);               // one reciprocal for both states
+            es_e = 611.21f * fast_ex2((22.587f * 1.4426950408889634f) * dTe * (rr * dp));
+            es_p = 611.21f * fast_ex2((22.587f * 1.4426950408889634f) * dTp * (rr * de));
+        } else {
+            const bool we = dTe >= 0.0f, wp = dTp >= 0.0f;
+            const float ce = we ? (273.0f - 32.19f) : (273.0f + 0.7f), cp = wp ? (273.0f - 32.19f) : (273.0f + 0.7f);
+            const float ae = we ? (17.502f * 1.4426950408889634f) : (22.587f * 1.4426950408889634f);
+            const float ap = wp ? (17.502f * 1.4426950408889634f) : (22.587f * 1.4426950408889634f);
+            const float de = tm273 + ce, dp = tkp + cp;
+            const float rr = fast_rcp(de * dp);
+            es_e = 611.21f * fast_ex2(ae * dTe * (rr * dp));
+            es_p = 611.21f * fast_ex2(ap * dTp * (rr * de));
+            if (!(dTe >= 0.0f || dTe <= -23.0f)) {            // mixed phase (or NaN): blend water/ice
                 const float ew = 611.21f * __expf(__fdividef(17.502f * dTe, tm273 + (273.0f - 32.19f)));
                 const float r = (dTe + 23.0f) * (1.0f / 23.0f), al = r * r;
                 es_e = al * ew + (1.0f - al) * es_e;
             }
-            if (mix_p) {
+            if (!(dTp >= 0.0f || dTp <= -23.0f)) {
                 const float ew = 611.21f * __expf(__fdividef(17.502f * dTp, tkp + (273.0f - 32.19f)));
                 const float r = (dTp + 23.0f) * (1.0f / 23.0f), al = r * r;
                 es_p = al * ew + (1.0f - al) * es_p;
@@ -300,10 +305,13 @@ pgw_column_kernel(const __grid_constant__ pgw_timestep_args a, const int lst, co
 
     // ---------------- phase 1: surface .. p_ref, parked in shared memory ----------------
     uint32_t off = (uint32_t)(L - 1) * n + c;
+    // T_pgw is parked as fp32.  Its rounding residual r_l (|r_l| <= 1.5e-5 K) enters the
+    // geopotential as Rd * sum_l r_l dlnp_l; that sum is taken once with the ERA pressures
+    // (its change over the iteration is < 1e-8 m2/s2) and added to every iteration's sum.
+    double acc_res = 0.0, t_low_d = 0.0;
     {
-        double *pT = st_T + (size_t)(L - 1 - lst) * NT + tid;
-        float *pe = st_e + (size_t)(L - 1 - lst) * NT + tid;
-        for (int l = L - 1; l >= lst; --l, off -= n, pT -= NT, pe -= NT) {
+        float2 *pTe = st_Te + (size_t)(L - 1 - lst) * NT + tid;
+        for (int l = L - 1; l >= lst; --l, off -= n, pTe -= NT) {
             __pipeline_wait_prior(kRing - 1);
             const float *slot = my_ring + slot_r * (4 * NT);
             const float t = slot[0], q = slot[NT], u = slot[2 * NT], v = slot[3 * NT];
@@ -312,15 +320,18 @@ pgw_column_kernel(const __grid_constant__ pgw_timestep_args a, const int lst, co
             float dta, e_pgw;
             level(l, off, t, q, u, v, dta, e_pgw);
             const double td = (double)t;
-            *pT = td + (double)dta;
-            *pe = e_pgw;
+            const float t_pgw = t + dta;
+            *pTe = make_float2(t_pgw, e_pgw);
+            if (l == L - 1) t_low_d = td + (double)dta;
             // geopotential of the ERA state (functions.py:128-189)
             if (era_open) {
                 const double2 hl = s_hl[l];
                 double pt = fma(PSd, hl.y, hl.x);
                 if (pt < pref) { pt = pref; era_open = false; }     // layer that contains p_ref (:174-179)
                 const double tv = fma(td, 0.61 * (double)q, td);
-                acc_era = fma(tv, ln_ratio<FAST>(pb_era, pt, lk), acc_era);
+                const double dl = ln_ratio<FAST>(pb_era, pt, lk);
+                acc_era = fma(tv, dl, acc_era);
+                acc_res = fma((td + (double)dta) - (double)t_pgw, dl, acc_res);
                 pb_era = pt;
             }
         }
@@ -328,9 +339,8 @@ pgw_column_kernel(const __grid_constant__ pgw_timestep_args a, const int lst, co
     const double fis = (double)__ldg(a.FIS + c);
     const double phi_era = fis + kRd * acc_era;
     const double gdzg = blend_f64(a.zg_ref, c) * kG;              // step_03:292-295
-    const double *const bT = st_T + (size_t)(L - 1 - lst) * NT + tid;   // lowest level of the stash
-    const float *const be = st_e + (size_t)(L - 1 - lst) * NT + tid;
-    const double t_low = *bT;                                     // ta_pgw on the lowest level
+    const float2 *const bTe = st_Te + (size_t)(L - 1 - lst) * NT + tid;  // lowest level of the stash
+    const double t_low = t_low_d;                                 // ta_pgw on the lowest level
 
     // ---------------- phase 2: surface-pressure fixed point (step_03:182-319) ----------------
     // The loads of the upper column are already in flight and overlap this phase.
@@ -348,16 +358,16 @@ pgw_column_kernel(const __grid_constant__ pgw_timestep_args a, const int lst, co
         // layers ltop..L-1 are entirely below p_ref for this ps; it moves by at most a level or two
         while (ltop > lst) { const double2 h = s_hl[ltop - 1]; if (fma(psn, h.y, h.x) >= pref) --ltop; else break; }
         while (ltop < L) { const double2 h = s_hl[ltop]; if (fma(psn, h.y, h.x) < pref) ++ltop; else break; }
-        double acc = 0.0;
-        const double *pT = bT;
-        const float *pe = be;
+        double acc = acc_res;
+        const float2 *pTe = bTe;
         int l = L - 1;
-#pragma unroll 2
-        for (; l >= ltop; --l, pT -= NT, pe -= NT) {
+#pragma unroll 4
+        for (; l >= ltop; --l, pTe -= NT) {
             const double2 hl = s_hl[l];
             const float2 m = s_m[l];
-            const float e = *pe;
-            const double Td = *pT;
+            const float2 te = *pTe;
+            const float e = te.y;
+            const double Td = (double)te.x;
             const double pt = fma(psn, hl.y, hl.x);
             // Tv = T (1 + 0.61 hus), hus = 0.622 e / (p - 0.378 e)   (functions.py:66-72, :144)
             const float g = fast_rcp(fmaf(-0.378f, e, fmaf(psn_f, m.y, m.x)));
@@ -367,8 +377,9 @@ pgw_column_kernel(const __grid_constant__ pgw_timestep_args a, const int lst, co
         }
         if (l >= lst && pb >= pref) {                              // layer that contains p_ref (:174-179)
             const float2 m = s_m[l];
-            const float e = *pe;
-            const double Td = *pT;
+            const float2 te = *pTe;
+            const float e = te.y;
+            const double Td = (double)te.x;
             const float g = fast_rcp(fmaf(-0.378f, e, fmaf(psn_f, m.y, m.x)));
             const double tv = fma(Td, (double)((0.61f * 0.622f) * e * g), Td);
             acc = fma(tv, ln_ratio<FAST>(pb, pref, lk), acc);
@@ -387,11 +398,11 @@ pgw_column_kernel(const __grid_constant__ pgw_timestep_args a, const int lst, co
     a.PS_out[c] = psn_f;
     a.dps_out[c] = (float)dps;
     {
-        const float *pe = be;
+        const float2 *pTe = bTe;
         uint32_t o2 = (uint32_t)(L - 1) * n + c;
-        for (int l = L - 1; l >= lst; --l, pe -= NT, o2 -= n) {
+        for (int l = L - 1; l >= lst; --l, pTe -= NT, o2 -= n) {
             const float2 m = s_m[l];
-            const float e = *pe;
+            const float e = pTe->y;
             st_stream(oQ + o2, 0.622f * e * fast_rcp(fmaf(-0.378f, e, fmaf(psn_f, m.y, m.x))));
         }
     }
@@ -490,7 +501,7 @@ int stash_top(const double *ak, const double *bk, int nlev, double p_ref, double
 
 size_t column_smem(int nlev, int nplev, int np, int nt) {
     return sizeof(double) * 2 * (size_t)(nlev + 1) +                       // (ak, bk)
-           (size_t)np * nt * (sizeof(double) + sizeof(float)) +            // T_pgw, e_pgw stash
+           (size_t)np * nt * (2 * sizeof(float)) +                         // (T_pgw, e_pgw) stash
            sizeof(float) * (size_t)(pgw::kRing + 1) * 4 * nt +             // cp.async ring
            sizeof(float) * 2 * (size_t)nlev + sizeof(float) * 3 * (size_t)nplev + 16;
 }
