@@ -23,12 +23,20 @@
 
 namespace pgw {
 
+// Raw (before, after) pair of a 2-D delta; all pairs of a column are loaded up front so
+// that their DRAM latencies overlap, then blended.
+struct Pair2 { float lo, hi; };
+__device__ __forceinline__ Pair2 load_pair(const pgw_tslab &s, uint32_t off) {
+    Pair2 r;
+    r.lo = __ldg(s.lo + off);
+    r.hi = __ldg(s.hi + off);      // == lo slab for an exact hit (x_new == 0)
+    return r;
+}
 // scipy interp1d._call_linear with x = [0, x_hi]: slope * x_new + y_lo (float64)
-__device__ __forceinline__ double blend_f64(const pgw_tslab &s, uint32_t off) {
-    const double lo = (double)__ldg(s.lo + off);
+__device__ __forceinline__ double blend_f64(const pgw_tslab &s, const Pair2 &v) {
+    const double lo = (double)v.lo;
     if (s.x_new == 0.0) return lo;
-    const double hi = (double)__ldg(s.hi + off);
-    return (hi - lo) / s.x_hi * s.x_new + lo;
+    return ((double)v.hi - lo) / s.x_hi * s.x_new + lo;
 }
 
 __device__ __forceinline__ float fast_rcp(float x) {
@@ -86,7 +94,8 @@ struct Walk2 {
     int lo;                 // index of the lo node; -1 once the target is above node 0
     float p_lo, inv_p_lo, inv_w;
     float a_lo, a_d, b_lo, b_d;
-    float a_n0, a_n1, b_n0, b_n1;
+    float a_n0, a_n1, b_n0, b_n1;     // raw slabs of node lo-1
+    float a_m0, a_m1, b_m0, b_m1;     // raw slabs of node lo-2 (loads issued two advances ahead)
 };
 
 struct Tslab32 { const float *lo, *hi; float w; };
@@ -154,22 +163,27 @@ pgw_column_kernel(const __grid_constant__ pgw_timestep_args a, const int lst, co
 
     // ---------------- surface, skin and soil (step_03:103-146) ----------------
     const float ps_f = __ldg(a.PS + c);
+    const Pair2 r_sic = load_pair(a.siconc, c), r_ts = load_pair(a.ts, c), r_tos = load_pair(a.tos, c);
+    const Pair2 r_psh = load_pair(a.ps_hist, c), r_tas = load_pair(a.tas, c), r_hurs = load_pair(a.hurs, c);
+    const Pair2 r_zg = load_pair(a.zg_ref, c);
+    const float r_ice = __ldg(a.FR_SEA_ICE + c), r_land = __ldg(a.FR_LAND + c), r_skin = __ldg(a.T_SKIN + c);
+    const float r_clim = __ldg(a.ts_clim + c), r_fis = __ldg(a.FIS + c);
     const double PSd = (double)ps_f;
     {
         // FR_SEA_ICE is float32 in the file and updated in place there
-        float sic = (float)((double)__ldg(a.FR_SEA_ICE + c) + blend_f64(a.siconc, c) / 100.0);
+        float sic = (float)((double)r_ice + blend_f64(a.siconc, r_sic) / 100.0);
         sic = sic < 0.0f ? 0.0f : (sic > 1.0f ? 1.0f : sic);           // np.clip keeps NaN
-        const double dts = blend_f64(a.ts, c);
-        const double dtos = blend_f64(a.tos, c);
+        const double dts = blend_f64(a.ts, r_ts);
+        const double dtos = blend_f64(a.tos, r_tos);
         double comb = dts;                                            // integrate_tos
         if (!isnan(sic) && !isnan(dtos)) {
-            float fr = sic + __ldg(a.FR_LAND + c);
+            float fr = sic + r_land;
             fr = fr < 0.0f ? 0.0f : (fr > 1.0f ? 1.0f : fr);
             comb = (double)fr * dts + (double)(1.0f - fr) * dtos;
         }
-        const double clim = (double)__ldg(a.ts_clim + c);
+        const double clim = (double)r_clim;
         a.FR_SEA_ICE_out[c] = sic;
-        a.T_SKIN_out[c] = (float)((double)__ldg(a.T_SKIN + c) + comb);
+        a.T_SKIN_out[c] = (float)((double)r_skin + comb);
         for (int s = 0; s < a.nsoil; ++s) {
             const double dso = clim + a.soil_decay[s] * (comb - clim);
             a.T_SO_out[(uint32_t)s * n + c] = (float)((double)__ldg(a.T_SO + (uint32_t)s * n + c) + dso);
@@ -193,7 +207,7 @@ pgw_column_kernel(const __grid_constant__ pgw_timestep_args a, const int lst, co
     {
         // replace_delta_sfc: node s carries (ps_hist, surface delta); the nodes after it all
         // hold the surface delta, so node s acts as the last node of the column.
-        const float psh = (float)blend_f64(a.ps_hist, c);
+        const float psh = (float)blend_f64(a.ps_hist, r_psh);
         int s = K - 1;
         if (!(psh > s_plev[K - 1])) {
             s = -1;
@@ -202,10 +216,12 @@ pgw_column_kernel(const __grid_constant__ pgw_timestep_args a, const int lst, co
         }
         if (s < 0) { errbits |= PGW_ERR_PS_HIST_RANGE; s = 0; }
         wA.lo = s; wA.p_lo = psh; wA.inv_p_lo = fast_rcp(psh); wA.inv_w = 0.0f;
-        wA.a_lo = (float)blend_f64(a.tas, c); wA.a_d = 0.0f;
-        wA.b_lo = (float)blend_f64(a.hurs, c); wA.b_d = 0.0f;
+        wA.a_lo = (float)blend_f64(a.tas, r_tas); wA.a_d = 0.0f;
+        wA.b_lo = (float)blend_f64(a.hurs, r_hurs); wA.b_d = 0.0f;
         wA.a_n0 = wA.a_n1 = wA.b_n0 = wA.b_n1 = 0.0f;
+        wA.a_m0 = wA.a_m1 = wA.b_m0 = wA.b_m1 = 0.0f;
         if (s >= 1) load_raw(v_ta, v_hur, s - 1, wA.a_n0, wA.a_n1, wA.b_n0, wA.b_n1);
+        if (s >= 2) load_raw(v_ta, v_hur, s - 2, wA.a_m0, wA.a_m1, wA.b_m0, wA.b_m1);
 
         float x0, x1, y0, y1;
         load_raw(v_ua, v_va, K - 1, x0, x1, y0, y1);
@@ -213,6 +229,8 @@ pgw_column_kernel(const __grid_constant__ pgw_timestep_args a, const int lst, co
         wB.a_lo = blend(v_ua.w, x0, x1); wB.a_d = 0.0f;
         wB.b_lo = blend(v_va.w, y0, y1); wB.b_d = 0.0f;
         load_raw(v_ua, v_va, K - 2, wB.a_n0, wB.a_n1, wB.b_n0, wB.b_n1);
+        wB.a_m0 = wB.a_m1 = wB.b_m0 = wB.b_m1 = 0.0f;
+        if (K >= 3) load_raw(v_ua, v_va, K - 3, wB.a_m0, wB.a_m1, wB.b_m0, wB.b_m1);
     }
     float min_src_p = (wA.lo == 0) ? wA.p_lo : s_plev[0];
 
@@ -227,7 +245,8 @@ pgw_column_kernel(const __grid_constant__ pgw_timestep_args a, const int lst, co
                 w.a_lo = blend(va.w, w.a_n0, w.a_n1); w.b_lo = blend(vb.w, w.b_n0, w.b_n1);
                 w.a_d = hi_a - w.a_lo; w.b_d = hi_b - w.b_lo;
                 w.inv_w = from_synth ? fast_rcp(fast_lg2(hi_p * w.inv_p_lo)) : s_inv_w[w.lo];
-                if (w.lo >= 1) load_raw(va, vb, w.lo - 1, w.a_n0, w.a_n1, w.b_n0, w.b_n1);
+                w.a_n0 = w.a_m0; w.a_n1 = w.a_m1; w.b_n0 = w.b_m0; w.b_n1 = w.b_m1;
+                if (w.lo >= 2) load_raw(va, vb, w.lo - 2, w.a_m0, w.a_m1, w.b_m0, w.b_m1);
             } else {
                 // above node 0: constant extrapolation with node 0's values; p_lo = 0 ends the walk
                 w.a_d = 0.0f; w.b_d = 0.0f; w.inv_w = 0.0f; w.p_lo = 0.0f; w.inv_p_lo = 1.0f;
@@ -247,8 +266,7 @@ pgw_column_kernel(const __grid_constant__ pgw_timestep_args a, const int lst, co
     float psn_f = ps_f;                             // ps used for QV; replaced after the iteration
 
     // One model level: deltas at p, RH of the ERA state, PGW state, outputs T/U/V.
-    auto level = [&](int l, uint32_t off, float t, float q, float u, float v, float &dta_out, float &e_pgw) {
-        const float2 m = s_m[l];
+    auto level = [&](const float2 m, uint32_t off, float t, float q, float u, float v, float &dta_out, float &e_pgw) {
         const float p = fmaf(ps_f, m.y, m.x);
         if (fmaxf(wA.p_lo, wB.p_lo) > p) {
             advance(wA, p, v_ta, v_hur);
@@ -315,10 +333,11 @@ pgw_column_kernel(const __grid_constant__ pgw_timestep_args a, const int lst, co
             __pipeline_wait_prior(kRing - 1);
             const float *slot = my_ring + slot_r * (4 * NT);
             const float t = slot[0], q = slot[NT], u = slot[2 * NT], v = slot[3 * NT];
+            const float2 m = s_m[l];
             slot_r = (slot_r == kRing) ? 0 : slot_r + 1;
             prefetch();
             float dta, e_pgw;
-            level(l, off, t, q, u, v, dta, e_pgw);
+            level(m, off, t, q, u, v, dta, e_pgw);
             const double td = (double)t;
             const float t_pgw = t + dta;
             *pTe = make_float2(t_pgw, e_pgw);
@@ -336,9 +355,9 @@ pgw_column_kernel(const __grid_constant__ pgw_timestep_args a, const int lst, co
             }
         }
     }
-    const double fis = (double)__ldg(a.FIS + c);
+    const double fis = (double)r_fis;
     const double phi_era = fis + kRd * acc_era;
-    const double gdzg = blend_f64(a.zg_ref, c) * kG;              // step_03:292-295
+    const double gdzg = blend_f64(a.zg_ref, r_zg) * kG;              // step_03:292-295
     const float2 *const bTe = st_Te + (size_t)(L - 1 - lst) * NT + tid;  // lowest level of the stash
     const double t_low = t_low_d;                                 // ta_pgw on the lowest level
 
@@ -410,11 +429,11 @@ pgw_column_kernel(const __grid_constant__ pgw_timestep_args a, const int lst, co
         __pipeline_wait_prior(kRing - 1);
         const float *slot = my_ring + slot_r * (4 * NT);
         const float t = slot[0], q = slot[NT], u = slot[2 * NT], v = slot[3 * NT];
+        const float2 m = s_m[l];
         slot_r = (slot_r == kRing) ? 0 : slot_r + 1;
         prefetch();
         float dta, e_pgw;
-        level(l, off, t, q, u, v, dta, e_pgw);
-        const float2 m = s_m[l];
+        level(m, off, t, q, u, v, dta, e_pgw);
         st_stream(oQ + off, 0.622f * e_pgw * fast_rcp(fmaf(-0.378f, e_pgw, fmaf(psn_f, m.y, m.x))));
     }
     __pipeline_wait_prior(0);
