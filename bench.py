@@ -48,39 +48,59 @@ def measured_peak_gbs():
         return 6650.0, "fallback"
 
 
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md): one
+    `nvidia-smi -lms 100` process runs across the region; samples are kept by wall-clock time."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        super().__init__(daemon=True)
-        self.gpu, self.rows, self.stop_flag = gpu_index, [], False
+        self.gpu, self.proc, self.t0, self.t1 = gpu_index, None, None, None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
 
-    def run(self):
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True,
-                                     timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
-            except Exception:
-                pass
-            time.sleep(0.2)
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_stop(self):
+        self.t1 = time.time()
 
     def summary(self):
-        sm = [float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        rows = []
+        if self.proc is not None:
+            time.sleep(0.25)
+            self.proc.terminate()
+            try:
+                out, _ = self.proc.communicate(timeout=5)
+            except Exception:
+                out = ""
+            for line in out.splitlines():
+                r = [x.strip() for x in line.split(",")]
+                if len(r) < 10:
+                    continue
+                try:
+                    ts = datetime.strptime(r[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                except ValueError:
+                    continue
+                rows.append((ts, r))
+        inside = [r for ts, r in rows if self.t0 is not None and self.t0 - 0.05 <= ts <= self.t1 + 0.15]
+        use = inside if inside else [r for _, r in rows]
+        num = lambda x: float(x) if x.replace(".", "", 1).isdigit() else None
+        sm = [num(r[2]) for r in use if num(r[2]) is not None]
+        mx = [num(r[3]) for r in use if num(r[3]) is not None]
         reasons = set()
-        for r in self.rows:
+        for r in use:
             for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
-                                 r[5:9]):
+                                 r[6:10]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.rows)}
+                "reasons": sorted(reasons), "samples": len(use), "samples_in_region": len(inside)}
 
 
 # --------------------------------------------------------------------------- CPU arm
@@ -216,7 +236,7 @@ def run_ours(a):
     eng.kernel_events = []
     launches0 = eng.stats["launches"]
     barrier()
-    sampler.start()
+    sampler.mark_start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     pend = None
@@ -228,7 +248,7 @@ def run_ours(a):
     n_iters.append(pend.result()["n_iter"])
     ev1.record()
     barrier()
-    sampler.stop_flag = True
+    sampler.mark_stop()
     ms = ev0.elapsed_time(ev1)
     kernel_ms = [e0.elapsed_time(e1) for e0, e1 in eng.kernel_events]
     eng.kernel_events = None
@@ -312,7 +332,7 @@ def run_ours(a):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--grid", default="GL", choices=sorted(GRIDS))

@@ -96,6 +96,35 @@ int pgw_specific_to_relative_humidity_f64(const double *hus, const double *pa, c
 int pgw_relative_to_specific_humidity_f64(const double *hur, const double *pa, const double *ta,
                                           double *hus, long long n, void *stream);
 
+/* The small helpers of the same block, elementwise over n values:
+ *   PGW_HUM_Q2E         specific_humidity_to_vapor_pressure(x=hus, y=pa)      functions.py:58-64
+ *   PGW_HUM_E2Q         vapor_pressure_to_specific_humidity(x=vapp, y=pa)     functions.py:66-72
+ *   PGW_HUM_ESAT_WATER  saturation_vapor_pressure_water_or_ice(x=ta, water)   functions.py:74-89
+ *   PGW_HUM_ESAT_ICE    saturation_vapor_pressure_water_or_ice(x=ta, ice)
+ *   PGW_HUM_ESAT_BLEND  saturation_vapor_pressure_water_and_ice(x=ta)         functions.py:91-105
+ * (y may be NULL for the three ESAT operations). */
+#define PGW_HUM_Q2E         0
+#define PGW_HUM_E2Q         1
+#define PGW_HUM_ESAT_WATER  2
+#define PGW_HUM_ESAT_ICE    3
+#define PGW_HUM_ESAT_BLEND  4
+int pgw_humidity_op_f32(int op, const float *x, const float *y, float *out, long long n, void *stream);
+int pgw_humidity_op_f64(int op, const double *x, const double *y, double *out, long long n, void *stream);
+
+/* ------------------------------------------------------------------------
+ * Surface insertion into the 3-D deltas, every column.
+ * Replaces replace_delta_sfc(source_P, ps_hist, delta, delta_sfc), functions.py:343-366,
+ * as applied through xr.apply_ufunc(vectorize=True), functions.py:396-402.
+ *   source_P [K, ncol] (or [K] if src_p_is_1d), ps_hist, delta_sfc [ncol], delta [K, ncol]
+ *   out_P, out_d [K, ncol];  err: PGW_ERR_PS_HIST_RANGE (the reference's bare ValueError)
+ * ---------------------------------------------------------------------- */
+int pgw_replace_delta_sfc_f32(const float *source_P, const float *ps_hist, const float *delta,
+                              const float *delta_sfc, float *out_P, float *out_d, int K,
+                              long long ncol, int src_p_is_1d, uint32_t *err, void *stream);
+int pgw_replace_delta_sfc_f64(const double *source_P, const double *ps_hist, const double *delta,
+                              const double *delta_sfc, double *out_P, double *out_d, int K,
+                              long long ncol, int src_p_is_1d, uint32_t *err, void *stream);
+
 /* ------------------------------------------------------------------------
  * Hydrostatic geopotential at a reference pressure.
  * Replaces integ_geopot(pa_hl, zgs, ta, hus, level1, p_ref), functions.py:128-189.

@@ -74,6 +74,10 @@ def _load():
         "pgw_relative_to_specific_humidity_f32": (i, [vp, vp, vp, vp, ll, vp]),
         "pgw_specific_to_relative_humidity_f64": (i, [vp, vp, vp, vp, ll, vp]),
         "pgw_relative_to_specific_humidity_f64": (i, [vp, vp, vp, vp, ll, vp]),
+        "pgw_humidity_op_f32": (i, [i, vp, vp, vp, ll, vp]),
+        "pgw_humidity_op_f64": (i, [i, vp, vp, vp, ll, vp]),
+        "pgw_replace_delta_sfc_f32": (i, [vp, vp, vp, vp, vp, vp, i, ll, i, vp, vp]),
+        "pgw_replace_delta_sfc_f64": (i, [vp, vp, vp, vp, vp, vp, i, ll, i, vp, vp]),
         "pgw_integ_geopot_f32": (i, [vp, vp, vp, vp, vp, d, vp, i, ll, vp, vp]),
         "pgw_integ_geopot_f64": (i, [vp, vp, vp, vp, vp, d, vp, i, ll, vp, vp]),
         "pgw_integrate_tos_f32": (i, [vp, vp, vp, vp, vp, ll, vp]),

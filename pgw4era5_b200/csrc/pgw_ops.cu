@@ -182,6 +182,63 @@ __global__ void time_mean_kernel(const float *__restrict__ series, int ntime, fl
     }
 }
 
+// ---------------------------------------------------------------------------
+// the small humidity helpers of functions.py:58-105 as one elementwise kernel
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void humidity_op_kernel(int op, const T *__restrict__ x, const T *__restrict__ y,
+                                   T *__restrict__ out, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        T r;
+        switch (op) {
+            case PGW_HUM_Q2E: r = x[i] * y[i] / (T(0.622) + T(0.378) * x[i]); break;              // :58-64
+            case PGW_HUM_E2Q: r = T(0.622) * x[i] / (y[i] - (T(1) - T(0.622)) * x[i]); break;     // :66-72
+            case PGW_HUM_ESAT_WATER:
+                r = T(611.21) * exp(T(17.502) * (x[i] - T(273.16)) / (x[i] - T(32.19))); break;  // :74-89
+            case PGW_HUM_ESAT_ICE:
+                r = T(611.21) * exp(T(22.587) * (x[i] - T(273.16)) / (x[i] - T(-0.7))); break;
+            default: r = esat_generic<T>(x[i]); break;                                           // :91-105
+        }
+        out[i] = r;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// replace_delta_sfc applied to every column (functions.py:343-366, :396-402)
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(128)
+replace_delta_sfc_kernel(const T *__restrict__ source_P, const T *__restrict__ ps_hist,
+                         const T *__restrict__ delta, const T *__restrict__ delta_sfc,
+                         T *__restrict__ out_P, T *__restrict__ out_d, int K, long long ncol, int src_1d,
+                         uint32_t *err) {
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncol) return;
+    const T *sp = src_1d ? source_P : source_P + c;
+    const long long ss = src_1d ? 1 : ncol;
+    const T ph = ps_hist[c], ds = delta_sfc[c];
+    T pmax = -INFINITY, pmin = INFINITY;
+    int sfc = -1;
+    for (int k = 0; k < K; ++k) {
+        const T p = sp[(long long)k * ss];
+        out_P[(long long)k * ncol + c] = p;
+        out_d[(long long)k * ncol + c] = delta[(long long)k * ncol + c];
+        pmax = p > pmax ? p : pmax;
+        pmin = p < pmin ? p : pmin;
+        if (ph > p) sfc = k;                       // np.max(np.argwhere(ps_hist > source_P))
+    }
+    if (ph > pmax) {                               // :356-359
+        out_P[(long long)(K - 1) * ncol + c] = ph;
+        out_d[(long long)(K - 1) * ncol + c] = ds;
+    } else if (ph < pmin || sfc < 0) {             // :360-361 and the empty argwhere of :363
+        atomicOr(err, PGW_ERR_PS_HIST_RANGE);
+    } else {                                       // :362-365
+        for (int k = sfc; k < K; ++k) out_d[(long long)k * ncol + c] = ds;
+        out_P[(long long)sfc * ncol + c] = ph;
+    }
+}
+
 inline unsigned ew_grid(long long n, int block) {
     long long g = (n + block - 1) / block;
     const long long cap = 148LL * 16;          // persistent-style: 16 CTAs per SM, grid-stride loop
@@ -252,6 +309,28 @@ PGW_GEOPOT(pgw_integ_geopot_f64, double)
     }
 PGW_TOS(pgw_integrate_tos_f32, float)
 PGW_TOS(pgw_integrate_tos_f64, double)
+
+#define PGW_HUMOP(NAME, T)                                                                           \
+    int NAME(int op, const T *x, const T *y, T *out, long long n, void *stream) {                    \
+        PGW_REQUIRE(x && out && n > 0 && op >= PGW_HUM_Q2E && op <= PGW_HUM_ESAT_BLEND);             \
+        PGW_REQUIRE(y || op >= PGW_HUM_ESAT_WATER);                                                  \
+        humidity_op_kernel<T><<<ew_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(op, x, y, out, n);  \
+        return pgw_check_launch("humidity_op_kernel");                                               \
+    }
+PGW_HUMOP(pgw_humidity_op_f32, float)
+PGW_HUMOP(pgw_humidity_op_f64, double)
+
+#define PGW_RDS(NAME, T)                                                                             \
+    int NAME(const T *source_P, const T *ps_hist, const T *delta, const T *delta_sfc, T *out_P,      \
+             T *out_d, int K, long long ncol, int src_p_is_1d, uint32_t *err, void *stream) {        \
+        PGW_REQUIRE(source_P && ps_hist && delta && delta_sfc && out_P && out_d && err);             \
+        PGW_REQUIRE(K >= 1 && ncol > 0);                                                             \
+        replace_delta_sfc_kernel<T><<<(unsigned)((ncol + 127) / 128), 128, 0, (cudaStream_t)stream>>>( \
+            source_P, ps_hist, delta, delta_sfc, out_P, out_d, K, ncol, src_p_is_1d, err);           \
+        return pgw_check_launch("replace_delta_sfc_kernel");                                         \
+    }
+PGW_RDS(pgw_replace_delta_sfc_f32, float)
+PGW_RDS(pgw_replace_delta_sfc_f64, double)
 
 int pgw_time_interp_f32(const float *lo, const float *hi, double x_hi, double x_new, float *out, long long n,
                         void *stream) {

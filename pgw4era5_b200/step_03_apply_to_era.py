@@ -1,0 +1,207 @@
+#!/usr/bin/python
+# -*- coding: utf-8 -*-
+"""
+PGW for ERA5, main routine: drop-in for the reference's ``step_03_apply_to_era.py``.
+
+Same command line (``-i -o -f -l -H -d -p -t -D``), same ``settings.py`` names, same file
+naming; the per-file work (step_03_apply_to_era.py:44-381 of the reference) runs as one fused
+CUDA pass per ERA5 file on a B200 through ``PGWEngine``.  ``-p N`` starts N worker processes,
+worker i bound to GPU i % device_count (the reference's pool of CPU workers, parallel.py).
+
+    python -m pgw4era5_b200.step_03_apply_to_era -i era_in -o era_out -d deltas \\
+           -f 2006080200 -l 2006080300 -H 3 -t
+"""
+import argparse
+import os
+from argparse import RawDescriptionHelpFormatter
+from datetime import datetime, timedelta
+from pathlib import Path
+
+import numpy as np
+
+from . import ncio, settings
+from .parallel import IterMP
+
+_ENGINES = {}
+
+
+def load_delta_set(delta_input_dir, device="cuda"):
+    """Read every delta file the path needs (ta, hur, ua, va, zg, tas, hurs, ts, tos, siconc as
+    SCEN-HIST, ps as HIST; step_03_apply_to_era.py:533-539) into one device-resident DeltaSet."""
+    from .engine import DeltaSet, VARS_2D, VARS_3D
+    deltas = {}
+    for name in VARS_3D + VARS_2D:
+        var_name, base = ("ps", settings.file_name_bases['HIST']) if name == "ps_hist" else \
+            (name, settings.file_name_bases['SCEN-HIST'])
+        ds = ncio.open_dataset(os.path.join(delta_input_dir, base.format(var_name)))
+        var = ds[var_name]
+        plev = None
+        if settings.PLEV_GCM in var.dims:
+            plev = np.asarray(ds[settings.PLEV_GCM].data, dtype=np.float64)
+        deltas[name] = dict(time=ncio.decode_time(ds[settings.TIME_GCM]), plev=plev, data=var.data)
+    return DeltaSet(deltas, device=device)
+
+
+def get_engine(delta_input_dir, era_file):
+    """One engine (and one resident copy of the climatology) per process and delta directory."""
+    import torch
+    from .engine import PGWEngine
+    ak = np.asarray(era_file['ak'].data)
+    bk = np.asarray(era_file['bk'].data)
+    key = (os.path.abspath(delta_input_dir), torch.cuda.current_device(), ak.tobytes(), bk.tobytes())
+    eng = _ENGINES.get(key)
+    if eng is None:
+        ds = load_delta_set(delta_input_dir, device=torch.device("cuda", torch.cuda.current_device()))
+        akm = np.asarray(era_file['akm'].data) if 'akm' in era_file else None      # step_03:68-85
+        bkm = np.asarray(era_file['bkm'].data) if 'bkm' in era_file else None
+        soil = np.asarray(era_file[settings.SOIL_HLEV_ERA].data) if settings.SOIL_HLEV_ERA in era_file else ()
+        eng = PGWEngine(ak, bk, ds, soil1=soil, akm=akm, bkm=bkm)
+        _ENGINES[key] = eng
+    return eng
+
+
+def pgw_for_era5(inp_era_file_path, out_era_file_path, delta_input_dir, era_step_dt,
+                 ignore_top_pressure_error, debug_mode=None):
+    """Same signature as the reference's pgw_for_era5 (step_03_apply_to_era.py:44-47)."""
+    import torch
+    vmap = settings.var_name_map
+    if settings.i_debug >= 0:
+        print('Start working on input file {}'.format(inp_era_file_path))
+    era_file = ncio.open_dataset(inp_era_file_path, decode_cf=False)
+    eng = get_engine(delta_input_dir, era_file)
+    names = dict(PS=vmap['ps'], FIS=vmap['zgs'], FR_LAND=vmap['sftlf'], FR_SEA_ICE=vmap['sic'],
+                 T_SKIN=vmap['ts'], T_SO=vmap['st'], T=vmap['ta'], QV=vmap['hus'], U=vmap['ua'], V=vmap['va'])
+    era = {k: torch.from_numpy(np.ascontiguousarray(era_file[v].data, dtype=np.float32))
+           for k, v in names.items()}
+    res = eng.apply(era, era_step_dt, ignore_top_pressure_error=ignore_top_pressure_error,
+                    file_name=inp_era_file_path)
+    host = {k: res[k].cpu().numpy() for k in ("PS", "T", "QV", "U", "V", "T_SKIN", "T_SO", "FR_SEA_ICE", "delta_ps")}
+
+    if debug_mode == 'interpolate_full':                                       # step_03:350-361
+        from . import functions as F
+        ak, bk = eng.ak, eng.bk
+        pa_era = (eng.akm[None, :, None, None] + era_file[vmap['ps']].data.astype(np.float64)[:, None]
+                  * eng.bkm[None, :, None, None])
+        rel_era = F.specific_to_relative_humidity(era_file[vmap['hus']].data.astype(np.float64), pa_era,
+                                                  era_file[vmap['ta']].data.astype(np.float64))
+        pa_pgw = eng.akm[None, :, None, None] + host["PS"].astype(np.float64)[:, None] * eng.bkm[None, :, None, None]
+        rel_pgw = F.specific_to_relative_humidity(host["QV"].astype(np.float64), pa_pgw, host["T"].astype(np.float64))
+        deltas = {'ps': host["delta_ps"], 'ta': host["T"] - era_file[vmap['ta']].data,
+                  'hur': (rel_pgw - rel_era).astype(np.float32), 'ua': host["U"] - era_file[vmap['ua']].data,
+                  'va': host["V"] - era_file[vmap['va']].data, 'st': host["T_SO"] - era_file[vmap['st']].data,
+                  'ts': host["T_SKIN"] - era_file[vmap['ts']].data}
+        for var_name, d in deltas.items():
+            print(var_name)
+            out_file_path = os.path.join(Path(out_era_file_path).parents[0],
+                                         '{}_delta_{}'.format(vmap[var_name], Path(out_era_file_path).name))
+            ref = era_file[vmap[var_name]]
+            out = ncio.Dataset()
+            for dname in ref.dims:
+                if dname in era_file:
+                    out[dname] = era_file[dname]
+            out[vmap[var_name]] = ncio.Variable(ref.dims, d.reshape(ref.data.shape))
+            out.to_netcdf(out_file_path, mode='w')
+    else:                                                                      # step_03:367-381
+        for key in ("PS", "T", "QV", "U", "V", "T_SKIN", "T_SO", "FR_SEA_ICE"):
+            ref = era_file[names[key]]
+            era_file[names[key]] = ncio.Variable(ref.dims, host[key].reshape(ref.data.shape).astype(ref.data.dtype),
+                                                 ref.attrs)
+        if vmap['hur'] in era_file:
+            del era_file[vmap['hur']]
+        era_file.to_netcdf(out_era_file_path, mode='w')
+        era_file.close()
+        if settings.i_debug >= 1:
+            print('Done. Saved to file {}.'.format(out_era_file_path))
+    return res["n_iter"]
+
+
+def debug_interpolate_time(inp_era_file_path, out_era_file_path, delta_input_dir, era_step_dt,
+                           ignore_top_pressure_error, debug_mode=None):
+    """step_03_apply_to_era.py:387-414: write the deltas interpolated in time only."""
+    from . import functions as F
+    era_file = ncio.open_dataset(inp_era_file_path, decode_cf=False)
+    for var_name in ['tos', 'tas', 'hurs', 'ps', 'ta', 'hur', 'ua', 'va', 'zg']:
+        print(var_name)
+        out_file_path = os.path.join(Path(out_era_file_path).parents[0],
+                                     '{}_{}_{}'.format("delta", var_name, Path(out_era_file_path).name))
+        delta = F.load_delta(delta_input_dir, var_name, era_file[settings.TIME_ERA].data,
+                             target_date_time=era_step_dt)
+        out = ncio.Dataset()
+        for d in delta.dims:
+            if d == settings.TIME_GCM:
+                out[d] = era_file[settings.TIME_ERA]
+            elif d in delta.coords:
+                out[d] = ncio.Variable((d,), delta.coords[d])
+        out[var_name] = ncio.Variable(delta.dims, delta.values)
+        out.to_netcdf(out_file_path, mode='w')
+    era_file.close()
+
+
+def build_parser():
+    parser = argparse.ArgumentParser(
+        description="Perturb ERA5 with PGW climate deltas on B200 GPUs. Settings can be made in "
+                    "settings.py (or a copy named by the PGW_SETTINGS environment variable). "
+                    "Adds the climate change signal for ua, va, ta (with tas near the surface), hus "
+                    "(from hur and hurs), skin/SST and soil temperature and sea ice, and iteratively "
+                    "updates ps so that the geopotential at the reference pressure changes by the zg "
+                    "climate delta.  See the reference's step_03_apply_to_era.py for the method.",
+        formatter_class=RawDescriptionHelpFormatter)
+    parser.add_argument('-i', '--input_dir', type=str, default=None,
+                        help='Directory with ERA5 input files to process (not overwritten).')
+    parser.add_argument('-o', '--output_dir', type=str, default=None,
+                        help='Directory to store processed ERA5 files.')
+    parser.add_argument('-f', '--first_era_step', type=str, default='2006080200',
+                        help='Date of first ERA5 time step to process. Format YYYYMMDDHH.')
+    parser.add_argument('-l', '--last_era_step', type=str, default='2006080300',
+                        help='Date of last ERA5 time step to process. Format YYYYMMDDHH.')
+    parser.add_argument('-H', '--hour_inc_step', type=int, default=3,
+                        help='Hourly increment of the ERA5 time steps to process.')
+    parser.add_argument('-d', '--delta_input_dir', type=str, default=None,
+                        help='Directory with GCM climate deltas (SCEN-HIST) for ta,hur,ua,va,zg,tas,hurs,'
+                             'ts,tos,siconc and the HIST climatology of ps, all on the ERA5 grid.')
+    parser.add_argument('-p', '--n_par', type=int, default=1,
+                        help='Number of parallel worker processes (one GPU each, round robin).')
+    parser.add_argument('-t', '--ignore_top_pressure_error', action='store_true',
+                        help='Ignore the error raised when the climate deltas reach up less far than ERA5.')
+    parser.add_argument('-D', '--debug_mode', type=str, default=None,
+                        help='"interpolate_time": store the deltas interpolated in time only; '
+                             '"interpolate_full": store the final deltas instead of the modified files.')
+    return parser
+
+
+def main(argv=None):
+    args = build_parser().parse_args(argv)
+    if args.input_dir is None:
+        raise ValueError('Input directory (-i) is required.')
+    if args.output_dir is None:
+        raise ValueError('Output directory (-o) is required.')
+    if args.delta_input_dir is None:
+        raise ValueError('Delta input directory (-d) is required.')
+    if args.debug_mode is not None and args.debug_mode not in ['interpolate_time', 'interpolate_full']:
+        raise ValueError('Invalid input for argument --debug_mode! Valid arguments are: '
+                         '"interpolate_time" or "interpolate_full"')
+    first_era_step = datetime.strptime(args.first_era_step, '%Y%m%d%H')
+    last_era_step = datetime.strptime(args.last_era_step, '%Y%m%d%H')
+    era_step_dts = np.arange(first_era_step, last_era_step + timedelta(hours=args.hour_inc_step),
+                             timedelta(hours=args.hour_inc_step)).tolist()
+    Path(args.output_dir).mkdir(parents=True, exist_ok=True)
+    IMP = IterMP(njobs=args.n_par, run_async=True)
+    fargs = dict(delta_input_dir=args.delta_input_dir,
+                 ignore_top_pressure_error=args.ignore_top_pressure_error, debug_mode=args.debug_mode)
+    step_args = []
+    for era_step_dt in era_step_dts:
+        print(era_step_dt)
+        name = settings.era5_file_name_base.format(era_step_dt)
+        step_args.append(dict(inp_era_file_path=os.path.join(args.input_dir, name),
+                              out_era_file_path=os.path.join(args.output_dir, name),
+                              era_step_dt=era_step_dt))
+    if (args.debug_mode is None) or (args.debug_mode == 'interpolate_full'):
+        run_function = pgw_for_era5
+    else:
+        run_function = debug_interpolate_time
+    IMP.run(run_function, fargs, step_args)
+    return IMP.output
+
+
+if __name__ == "__main__":
+    main()

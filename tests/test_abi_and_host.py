@@ -1,0 +1,173 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol the header declares;
+host logic (calendar brackets, regrid tables, partitioning, NetCDF shim) against the oracle."""
+import os
+import re
+from datetime import datetime
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "pgw_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(pgw_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    import ctypes
+    from pgw4era5_b200 import _native as N
+    lib = ctypes.CDLL(N.LIB_PATH)
+    declared = _declared_symbols()
+    assert len(declared) >= 25
+    for name in declared:
+        assert hasattr(lib, name), "libpgw_b200.so does not export %s" % name
+    # and the Python binding covers all of them
+    assert set(declared) <= set(N.EXPORTED) | {"pgw_version", "pgw_last_error"}
+    assert N.lib.pgw_version().startswith(b"pgw_b200")
+    assert N.lib.pgw_sizeof_timestep_args() == ctypes.sizeof(N.TimestepArgs)
+
+
+def test_invalid_arguments_are_rejected_without_a_gpu():
+    from pgw4era5_b200 import _native as N
+    assert N.lib.pgw_time_mean_f32(None, 12, None, 10, None) == N.PGW_E_INVALID
+    assert N.lib.pgw_interp_logp_f32(None, None, None, None, 1, 2, 3, 4, 0, 0, 2, None, None) == N.PGW_E_INVALID
+    assert N.lib.pgw_smooth_harmonic_f32(None, None, 365, 10, None) == N.PGW_E_INVALID
+    assert N.lib.pgw_timestep(None, None) == N.PGW_E_INVALID
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from pgw4era5_b200 import functions as F
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        F.specific_to_relative_humidity(np.ones(3), np.ones(3), np.ones(3))
+
+
+@pytest.mark.parametrize("when", [datetime(2006, 8, 2, 6), datetime(2006, 1, 1, 0), datetime(2006, 12, 31, 18),
+                                  datetime(2006, 3, 16, 12), datetime(2008, 2, 29, 6), datetime(2007, 1, 16, 12)])
+def test_time_bracket_matches_oracle(when):
+    from oracle import pgw_oracle as O
+    from pgw4era5_b200 import synthetic as S, timeinterp as TI
+    stamps = S.monthly_stamps()
+    b = TI.bracket(stamps[TI.drop_leap_day(stamps)], when)
+    keep, ib, ia, x_hi, x_new = O.delta_time_bracket(stamps, when)
+    assert (b.ind_before, b.ind_after) == (ib, ia)
+    if ib != ia:
+        assert (b.x_hi, b.x_new) == (x_hi, x_new)
+    else:
+        assert b.exact and b.x_new == 0.0
+
+
+def test_leap_day_dropped_from_daily_series():
+    from oracle import pgw_oracle as O
+    from pgw4era5_b200 import timeinterp as TI
+    days = np.datetime64("2000-01-01T12", "ns") + np.arange(366) * np.timedelta64(86400 * 10 ** 9, "ns")
+    keep = TI.drop_leap_day(days)
+    assert len(keep) == 365 and 59 not in keep
+    assert keep == O.delta_time_bracket(days, datetime(2003, 3, 1, 0))[0]
+    b = TI.bracket(days[keep], datetime(2003, 2, 28, 18))
+    k2, ib, ia, x_hi, x_new = O.delta_time_bracket(days, datetime(2003, 2, 28, 18))
+    assert (b.ind_before, b.ind_after, b.x_hi, b.x_new) == (ib, ia, x_hi, x_new)
+
+
+def _emulate_gather(data, tb):
+    pm0 = data[..., 0, :].mean(-1, dtype=np.float64).astype(np.float32).astype(np.float64)
+    pm1 = data[..., -1, :].mean(-1, dtype=np.float64).astype(np.float32).astype(np.float64)
+
+    def at(j, i):
+        out = np.empty(data.shape[:-2] + (len(j), len(i)))
+        for a, jj in enumerate(j):
+            for b, ii in enumerate(i):
+                out[..., a, b] = pm0 if jj == -1 else (pm1 if jj == -2 else data[..., jj, ii])
+        return out
+    a0, a1 = at(tb["j0"], tb["i0"]), at(tb["j1"], tb["i0"])
+    b0, b1 = at(tb["j0"], tb["i1"]), at(tb["j1"], tb["i1"])
+    wy, wx = tb["wy"][:, None], tb["wx"][None, :]
+    a = (a1 - a0) * wy + a0
+    b = (b1 - b0) * wy + b0
+    return (b - a) * wx + a
+
+
+GRID_CASES = [
+    # global 10 degree GCM -> coarse "ERA5" incl. poles, 0..360 both
+    (np.linspace(-85, 85, 18), np.arange(0.0, 360, 10.0), np.linspace(-90, 90, 25), np.arange(0, 360, 7.5)),
+    # GCM on -180..180, target 0..360: periodic wrap to the east
+    (np.linspace(-85, 85, 18), np.arange(-180.0, 180, 10.0), np.linspace(-60, 60, 13), np.arange(0, 360, 7.5)),
+    # GCM on 0..360, target -180..180: periodic wrap to the west
+    (np.linspace(-85, 85, 18), np.arange(0.0, 360, 10.0), np.linspace(-60, 60, 13), np.arange(-180, 180, 7.5)),
+    # regional, descending source latitude
+    (np.linspace(85, 20, 14), np.arange(-30.0, 61, 5.0), np.linspace(30, 80, 11), np.linspace(-20, 50, 15)),
+]
+
+
+@pytest.mark.parametrize("case", range(len(GRID_CASES)))
+def test_regrid_tables_match_oracle(case):
+    from oracle import pgw_oracle as O
+    from pgw4era5_b200 import functions as F
+    lat, lon, tlat, tlon = GRID_CASES[case]
+    rng = np.random.default_rng(case)
+    data = rng.normal(size=(2, len(lat), len(lon))).astype(np.float32)
+    ref = O.regrid_lat_lon(data, lat, lon, tlat, tlon)
+    got = _emulate_gather(data.astype(np.float64), F.regrid_tables(lat, lon, tlat, tlon))
+    assert not np.isnan(ref).any()
+    np.testing.assert_allclose(got, ref, rtol=0, atol=2e-7)
+
+
+def test_regrid_bounds_errors():
+    from pgw4era5_b200 import functions as F
+    lat, lon = np.linspace(20, 60, 9), np.arange(0.0, 41, 5.0)
+    with pytest.raises(ValueError, match="North or South"):
+        F.regrid_tables(lat, lon, np.linspace(10, 50, 5), np.linspace(5, 35, 4))
+    with pytest.raises(ValueError, match="East or West"):
+        F.regrid_tables(lat, lon, np.linspace(25, 50, 5), np.linspace(5, 75, 4))
+    # the reference's quirk: a descending-latitude global GCM grid gets no pole rows (dlat < 0)
+    with pytest.raises(ValueError, match="North or South"):
+        F.regrid_tables(np.linspace(85, -85, 18), np.arange(0.0, 360, 10), np.linspace(-90, 90, 7), np.arange(0, 360, 30.))
+
+
+def test_partitioning():
+    from pgw4era5_b200 import parallel as P
+    bands = P.split_rows(721, 8)
+    assert bands[0] == (0, 90) and bands[-1] == (630, 721)
+    assert sum(b - a for a, b in bands) == 721
+    assert all(bands[i][1] == bands[i + 1][0] for i in range(7))
+    seen = sorted(sum((P.timesteps_for_rank(124, r, 8) for r in range(8)), []))
+    assert seen == list(range(124))
+    assert P.decide_n_iter([270.0, 40.0, 5.9, 0.87, 0.139], 0.15) == 5
+    assert P.decide_n_iter([270.0, 40.0], 0.15) == 0
+    assert P.decide_n_iter([float("nan")], 0.15) == 1      # NaN > thresh is False: loop ends (step_03:189)
+
+
+def test_netcdf_roundtrip(tmp_path):
+    from pgw4era5_b200 import ncio
+    ds = ncio.Dataset()
+    ds["time"] = ncio.Variable(("time",), np.array([1.5]), {"units": "hours since 2006-08-02 00:00:00"})
+    ds["lat"] = ncio.Variable(("lat",), np.linspace(30, 32, 3))
+    ds["lon"] = ncio.Variable(("lon",), np.linspace(5, 8, 4))
+    ds["PS"] = ncio.Variable(("time", "lat", "lon"), np.arange(12, dtype=np.float32).reshape(1, 3, 4), {"units": "Pa"})
+    path = str(tmp_path / "x.nc")
+    ds.to_netcdf(path)
+    back = ncio.open_dataset(path)
+    assert back["PS"].dims == ("time", "lat", "lon") and back["PS"].data.dtype == np.float32
+    np.testing.assert_array_equal(back["PS"].data, ds["PS"].data)
+    assert back["PS"].attrs["units"] == "Pa"
+    t = ncio.decode_time(back["time"])
+    assert t[0] == np.datetime64("2006-08-02T01:30:00", "ns")
+    noleap = ncio.Variable(("time",), np.array([59.0, 365.0]), {"units": "days since 2001-01-01", "calendar": "noleap"})
+    assert list(ncio.decode_time(noleap)) == [np.datetime64("2001-03-01", "ns"), np.datetime64("2002-01-01", "ns")]
+
+
+def test_settings_surface():
+    from pgw4era5_b200 import settings, constants
+    assert (constants.CON_RD, constants.CON_G, constants.CON_MW_MD) == (287.05, 9.80665, 0.622)
+    assert settings.p_ref_inp == 30000 and settings.adj_factor == 0.95
+    assert settings.thresh_phi_ref_max_error == 0.15 and settings.max_n_iter == 20 and settings.i_reinterp == 0
+    assert settings.var_name_map["hus"] == "QV" and settings.era5_file_name_base.format(datetime(2006, 8, 2, 6)) == \
+        "cas20060802060000.nc"
+    from pgw4era5_b200.step_03_apply_to_era import build_parser
+    a = build_parser().parse_args(["-i", "a", "-o", "b", "-d", "c", "-t", "-p", "2", "-H", "6"])
+    assert a.ignore_top_pressure_error and a.n_par == 2 and a.hour_inc_step == 6 and a.first_era_step == "2006080200"

@@ -1,0 +1,113 @@
+"""The drop-in command lines end to end: NetCDF in -> CUDA pass -> NetCDF out, checked against
+the oracle (step_03) and against the array operators (step_02)."""
+import os
+from datetime import datetime
+
+import numpy as np
+import pytest
+import torch
+
+from cases import TOL, make_case, run_oracle
+from pgw4era5_b200 import ncio, settings, synthetic as S
+
+pytestmark = pytest.mark.gpu
+
+
+def _write_era(path, era, when):
+    e = S.to_numpy(era)
+    ds = ncio.Dataset()
+    hours = (np.datetime64(when, "ns") - np.datetime64("2006-08-01T00", "ns")) / np.timedelta64(1, "h")
+    ds["time"] = ncio.Variable(("time",), np.array([float(hours)]), {"units": "hours since 2006-08-01 00:00:00"})
+    ds["lat"] = ncio.Variable(("lat",), e["lat"]); ds["lon"] = ncio.Variable(("lon",), e["lon"])
+    ds["level"] = ncio.Variable(("level",), np.arange(1, 138, dtype=np.float64))
+    ds["level1"] = ncio.Variable(("level1",), np.arange(1, 139, dtype=np.float64))
+    ds["soil1"] = ncio.Variable(("soil1",), e["soil1"])
+    ds["ak"] = ncio.Variable(("level1",), e["ak"]); ds["bk"] = ncio.Variable(("level1",), e["bk"])
+    for name in ("PS", "FIS", "FR_LAND", "FR_SEA_ICE", "T_SKIN"):
+        ds[name] = ncio.Variable(("time", "lat", "lon"), e[name])
+    ds["T_SO"] = ncio.Variable(("time", "soil1", "lat", "lon"), e["T_SO"])
+    for name in ("T", "QV", "U", "V"):
+        ds[name] = ncio.Variable(("time", "level", "lat", "lon"), e[name])
+    ds.to_netcdf(path)
+
+
+def _write_deltas(ddir, deltas, lat, lon):
+    d = S.to_numpy(deltas)
+    for name, v in d.items():
+        var, base = ("ps", settings.file_name_bases["HIST"]) if name == "ps_hist" else (name, settings.file_name_bases["SCEN-HIST"])
+        ds = ncio.Dataset()
+        ds["time"] = ncio.encode_time(v["time"], "days since 1850-01-01 00:00:00")
+        ds["lat"] = ncio.Variable(("lat",), lat); ds["lon"] = ncio.Variable(("lon",), lon)
+        if v["plev"] is not None:
+            ds["plev"] = ncio.Variable(("plev",), v["plev"])
+            ds[var] = ncio.Variable(("time", "plev", "lat", "lon"), v["data"])
+        else:
+            ds[var] = ncio.Variable(("time", "lat", "lon"), v["data"])
+        ds.to_netcdf(os.path.join(ddir, base.format(var)))
+        if name == "ps_hist":      # step_02 writes HIST and SCEN-HIST for every variable; -D interpolate_time
+            ds.to_netcdf(os.path.join(ddir, settings.file_name_bases["SCEN-HIST"].format(var)))   # reads ps_delta
+
+
+def test_step_03_cli_matches_oracle(tmp_path):
+    from pgw4era5_b200 import step_03_apply_to_era as S3
+    when = datetime(2006, 8, 2, 6)
+    era, deltas = make_case(10, 24, 51)
+    inp, out, dd = tmp_path / "in", tmp_path / "out", tmp_path / "deltas"
+    for p in (inp, dd):
+        p.mkdir()
+    name = settings.era5_file_name_base.format(when)
+    _write_era(str(inp / name), era, when)
+    _write_deltas(str(dd), deltas, era["lat"], era["lon"])
+    old = settings.i_debug
+    settings.i_debug = 0
+    try:
+        n_iters = S3.main(["-i", str(inp), "-o", str(out), "-d", str(dd), "-f", "2006080206", "-l", "2006080206",
+                           "-H", "6", "-t"])
+    finally:
+        settings.i_debug = old
+    ref = run_oracle(era, deltas, when=when)
+    assert n_iters == [ref["n_iter"]]
+    res = ncio.open_dataset(str(out / name))
+    for key in ("PS", "T", "QV", "U", "V", "T_SKIN", "T_SO", "FR_SEA_ICE"):
+        g = res[key].data.astype(np.float64)
+        r = np.asarray(ref[key], dtype=np.float64).reshape(g.shape)
+        assert np.array_equal(np.isnan(g), np.isnan(r))
+        assert np.nanmax(np.abs(g - r)) <= TOL[key], key
+    assert "RELHUM" not in res and res["T"].dims == ("time", "level", "lat", "lon")
+    # --debug_mode interpolate_time writes the time-interpolated deltas (step_03:387-414)
+    S3.main(["-i", str(inp), "-o", str(out), "-d", str(dd), "-f", "2006080206", "-l", "2006080206", "-H", "6",
+             "-D", "interpolate_time"])
+    from oracle import pgw_oracle as O
+    dta = ncio.open_dataset(str(out / ("delta_ta_" + name)))["ta"].data
+    np.testing.assert_allclose(dta, O.load_delta(S.to_numpy(deltas)["ta"], when), rtol=0, atol=1e-6)
+
+
+def test_step_02_cli(tmp_path):
+    from oracle import pgw_oracle as O
+    from pgw4era5_b200 import step_02_preproc_deltas as S2
+    rng = np.random.default_rng(61)
+    lat, lon = np.linspace(-85, 85, 18), np.arange(0.0, 360, 10.0)
+    tlat, tlon = np.linspace(-90, 90, 37), np.arange(0.0, 360, 5.0)
+    gdir, sdir, rdir = tmp_path / "gcm", tmp_path / "smooth", tmp_path / "regrid"
+    gdir.mkdir()
+    stamps = np.datetime64("2001-01-01T12", "ns") + np.arange(365) * np.timedelta64(86400 * 10 ** 9, "ns")
+    data = (rng.normal(size=(365, 3, 18, 36)) + 2).astype(np.float32)
+    for base in settings.file_name_bases.values():
+        ds = ncio.Dataset()
+        ds["time"] = ncio.encode_time(stamps, "days since 1850-01-01 00:00:00")
+        ds["plev"] = ncio.Variable(("plev",), np.array([85000., 50000., 30000.]))
+        ds["lat"] = ncio.Variable(("lat",), lat); ds["lon"] = ncio.Variable(("lon",), lon)
+        ds["ta"] = ncio.Variable(("time", "plev", "lat", "lon"), data)
+        ds.to_netcdf(str(gdir / base.format("ta")))
+    era = ncio.Dataset()
+    era["lat"] = ncio.Variable(("lat",), tlat); era["lon"] = ncio.Variable(("lon",), tlon)
+    era.to_netcdf(str(tmp_path / "era.nc"))
+    S2.main(["smoothing", "-i", str(gdir), "-o", str(sdir), "-e", str(tmp_path / "era.nc"), "-v", "ta"])
+    sm = ncio.open_dataset(str(sdir / "ta_delta.nc"))["ta"].data
+    ref_s = O.filter_data_fast(data)
+    np.testing.assert_allclose(sm, ref_s, rtol=0, atol=2e-6)
+    S2.main(["regridding", "-i", str(sdir), "-o", str(rdir), "-e", str(tmp_path / "era.nc"), "-v", "ta"])
+    rg = ncio.open_dataset(str(rdir / "ta_historical.nc"))
+    assert rg["ta"].data.shape == (365, 3, 37, 72)
+    np.testing.assert_allclose(rg["ta"].data, O.regrid_lat_lon(sm, lat, lon, tlat, tlon), rtol=0, atol=1e-6)
+    np.testing.assert_array_equal(rg["lat"].data, tlat)

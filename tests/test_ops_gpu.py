@@ -1,0 +1,180 @@
+"""Parity of the stand-alone operators (functions.py drop-in, through the C ABI) against the
+golden vectors of the reference and against the fp64 oracle."""
+import numpy as np
+import pytest
+
+from oracle import pgw_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def F():
+    from pgw4era5_b200 import functions
+    return functions
+
+
+@pytest.mark.parametrize("mode", ["linear", "constant", "nan"])
+def test_interp_extrap_1d_golden(F, golden, mode):
+    out = F.interp_extrap_1d(golden["ie1_src_x"], golden["ie1_src_y"], golden["ie1_targ_x"], mode)
+    np.testing.assert_allclose(out, golden["ie1_out_" + mode], rtol=0, atol=1e-14, equal_nan=True)
+
+
+def test_interp_extrap_1d_off(F, golden):
+    out = F.interp_extrap_1d(golden["ie1_src_x"], golden["ie1_src_y"], golden["ie1_targ_inner"], "off")
+    np.testing.assert_allclose(out, golden["ie1_out_off_inner"], rtol=0, atol=1e-14)
+    with pytest.raises(ValueError, match="Extrapolation deactivated"):
+        F.interp_extrap_1d(golden["ie1_src_x"], golden["ie1_src_y"], golden["ie1_targ_x"], "off")
+
+
+@pytest.mark.parametrize("mode", ["linear", "constant", "nan"])
+def test_interp_1d_for_timelatlon_golden(F, golden, mode):
+    sp, tp, val = golden["i4_src_p"], golden["i4_targ_p"], golden["i4_val"]
+    out = np.zeros_like(tp)
+    F.interp_1d_for_timelatlon(val, sp, tp, out, tp.shape[0], tp.shape[2], tp.shape[3], mode)
+    ref = golden["i4_out_" + mode]
+    np.testing.assert_array_equal(np.isnan(out), np.isnan(ref))
+    np.testing.assert_allclose(out, ref, rtol=0, atol=1e-13, equal_nan=True)      # float64, same formula
+
+
+def test_interp_errors(F, golden):
+    sp, tp, val = golden["i4_src_p"], golden["i4_targ_p"], golden["i4_val"]
+    out = np.zeros_like(tp)
+    with pytest.raises(ValueError, match="Source pressure"):
+        F.interp_1d_for_timelatlon(val, np.ascontiguousarray(sp[:, ::-1]), tp, out, 2, 5, 6, "constant")
+    with pytest.raises(ValueError, match="Target pressure"):
+        F.interp_1d_for_timelatlon(val, sp, np.ascontiguousarray(tp[:, ::-1]), out, 2, 5, 6, "constant")
+    with pytest.raises(ValueError, match="Invalid input"):
+        F.interp_logp_4d(val, np.exp(sp), np.exp(tp), extrapolate="bogus")
+    with pytest.raises(ValueError, match="Lat dimension"):
+        F.interp_logp_4d(val, np.exp(sp), np.exp(tp)[:, :, :4], extrapolate="constant")
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-12), (np.float32, 1e-4)])
+def test_interp_logp_4d_vs_oracle(F, dtype, tol):
+    from pgw4era5_b200 import synthetic as S
+    rng = np.random.default_rng(5)
+    nt, ks, kt, ny, nx = 1, 19, 137, 9, 33
+    # source: plev19 jittered per column; target: hybrid model levels for random surface pressures
+    sp = np.sort(S.PLEV19[None, :, None, None] * rng.uniform(0.97, 1.03, (nt, ks, ny, nx)), axis=1)
+    ak, bk = S.hybrid_coefficients()
+    akm, bkm = 0.5 * (ak[1:] + ak[:-1]), 0.5 * (bk[1:] + bk[:-1])
+    tp = akm[None, :, None, None] + rng.uniform(6e4, 1.05e5, (nt, 1, ny, nx)) * bkm[None, :, None, None]
+    val = rng.normal(size=(nt, ks, ny, nx))
+    ref = O.interp_logp_4d(val.astype(dtype), sp.astype(dtype), tp.astype(dtype), "constant")
+    out = F.interp_logp_4d(val.astype(dtype), sp.astype(dtype), tp.astype(dtype), "constant")
+    assert out.dtype == dtype
+    np.testing.assert_allclose(out, ref, rtol=0, atol=tol)
+    # 1-D pressure-level table shared by all columns
+    plev = np.sort(rng.uniform(100., 1.0e5, ks))
+    ref1 = O.interp_logp_4d(val, np.broadcast_to(plev[None, :, None, None], val.shape).copy(), tp, "linear")
+    out1 = F.interp_logp_4d(val, plev, tp, "linear")
+    np.testing.assert_allclose(out1, ref1, rtol=0, atol=1e-11)
+
+
+def test_humidity_golden_and_oracle(F, golden):
+    hus, pa, ta = golden["hum_hus"], golden["hum_pa"], golden["hum_ta"]
+    np.testing.assert_allclose(F.specific_humidity_to_vapor_pressure(hus, pa), golden["hum_e"], rtol=1e-15)
+    np.testing.assert_allclose(F.vapor_pressure_to_specific_humidity(golden["hum_e"], pa), golden["hum_q"], rtol=1e-15)
+    np.testing.assert_allclose(F.saturation_vapor_pressure_water_or_ice(pa, ta, True), golden["hum_esw"], rtol=1e-14)
+    np.testing.assert_allclose(F.saturation_vapor_pressure_water_or_ice(pa, ta, False), golden["hum_esi"], rtol=1e-14)
+    ta2 = np.concatenate([ta, [250.16, 273.16, 260.0, np.nan]])
+    np.testing.assert_allclose(F.saturation_vapor_pressure_water_and_ice(None, ta2),
+                               O.saturation_vapor_pressure_water_and_ice(None, ta2), rtol=1e-14, equal_nan=True)
+    rh = O.specific_to_relative_humidity(hus, pa, ta)
+    np.testing.assert_allclose(F.specific_to_relative_humidity(hus, pa, ta), rh, rtol=1e-13)
+    np.testing.assert_allclose(F.relative_to_specific_humidity(rh, pa, ta), hus, rtol=1e-12)
+    f32 = F.specific_to_relative_humidity(hus.astype(np.float32), pa.astype(np.float32), ta.astype(np.float32))
+    assert f32.dtype == np.float32
+    np.testing.assert_allclose(f32, rh, rtol=2e-5)
+
+
+def test_integ_geopot_vs_oracle(F):
+    from pgw4era5_b200 import synthetic as S
+    era = S.to_numpy(S.make_era5(6, 20, 31))
+    ak, bk = era["ak"], era["bk"]
+    pa_hl = ak[None, :, None, None] + era["PS"].astype(np.float64)[:, None] * bk[None, :, None, None]
+    ref = O.integ_geopot(pa_hl, era["FIS"], era["T"], era["QV"], 30000.0)
+    out = F.integ_geopot(pa_hl, era["FIS"].astype(np.float64), era["T"].astype(np.float64),
+                         era["QV"].astype(np.float64), None, 30000.0)
+    np.testing.assert_allclose(out, ref, rtol=0, atol=1e-8)
+    pref = np.where(era["PS"] > 90000, 50000.0, 30000.0)
+    np.testing.assert_allclose(F.integ_geopot(pa_hl, era["FIS"].astype(np.float64), era["T"].astype(np.float64),
+                                              era["QV"].astype(np.float64), None, pref),
+                               O.integ_geopot(pa_hl, era["FIS"], era["T"], era["QV"], pref), rtol=0, atol=1e-8)
+    with pytest.raises(ValueError, match="below the surface"):
+        F.integ_geopot(pa_hl, era["FIS"].astype(np.float64), era["T"].astype(np.float64),
+                       era["QV"].astype(np.float64), None, 120000.0)
+
+
+def test_integrate_tos_golden(F, golden):
+    out = F.integrate_tos(golden["it_tos"], golden["it_ts"], golden["it_land"], golden["it_ice"])
+    np.testing.assert_allclose(out, golden["it_out"], rtol=0, atol=1e-15)
+    small = F.integrate_tos(np.array([[1., np.nan]]), np.array([[2., 3.]]), np.array([[.2, .5]]), np.array([[.1, 0.]]))
+    np.testing.assert_allclose(small, [[1.3, 3.0]], rtol=0, atol=1e-15)
+
+
+def test_replace_delta_sfc_golden(F, golden):
+    plev = golden["rds_plev"]
+    delta = np.arange(19.)
+    for i, ph in enumerate(golden["rds_ps_hist"]):
+        P, D = F.replace_delta_sfc(plev, ph, delta, 99.0)
+        np.testing.assert_array_equal(P, golden["rds_P_%d" % i])
+        np.testing.assert_array_equal(D, golden["rds_D_%d" % i])
+    for bad in (50.0, 100.0, np.nan):
+        with pytest.raises(ValueError):
+            F.replace_delta_sfc(plev, bad, delta, 99.0)
+
+
+def test_vert_interp_delta_vs_oracle(F):
+    from pgw4era5_b200 import synthetic as S
+    from cases import make_case, ERA_DATE
+    era, deltas = make_case(7, 21, 41)
+    e, d = S.to_numpy(era), S.to_numpy(deltas)
+    pa = e["akm"][None, :, None, None] + e["PS"].astype(np.float64)[:, None] * e["bkm"][None, :, None, None]
+    ta = O.load_delta(d["ta"], ERA_DATE); tas = O.load_delta(d["tas"], ERA_DATE); psh = O.load_delta(d["ps_hist"], ERA_DATE)
+    ref = O.vert_interp_delta(ta, d["ta"]["plev"], pa, tas, psh, True)
+    out = F.vert_interp_delta(ta, pa, tas, psh, True, plev=d["ta"]["plev"])
+    np.testing.assert_allclose(out, ref, rtol=0, atol=1e-11)
+    ref2 = O.vert_interp_delta(ta, d["ta"]["plev"], pa, None, None, True)
+    np.testing.assert_allclose(F.vert_interp_delta(ta, pa, None, None, True, plev=d["ta"]["plev"]), ref2, rtol=0, atol=1e-11)
+    with pytest.raises(ValueError, match="top pressure"):
+        F.vert_interp_delta(ta, pa, tas, psh, False, plev=d["ta"]["plev"])
+
+
+def test_smoothing_vs_oracle_and_golden(F, golden):
+    np.testing.assert_allclose(F.harmonic_ac_analysis(golden["hac_in"]), golden["hac_out"], rtol=0, atol=2e-6)
+    rng = np.random.default_rng(8)
+    x = (rng.normal(size=(365, 3, 5, 7)) + 3.0).astype(np.float32)
+    x[:, 1, 2, 3] = np.nan
+    x[17, 0, 0, 0] = np.nan
+    ref = O.filter_data_fast(x)
+    out = F.smooth_annual_cycle(x)
+    assert out.dtype == np.float32
+    np.testing.assert_array_equal(np.isnan(out), np.isnan(ref))
+    np.testing.assert_allclose(out, ref, rtol=0, atol=2e-6, equal_nan=True)
+    x12 = rng.normal(size=(12, 4, 6)).astype(np.float32)
+    np.testing.assert_allclose(F.smooth_annual_cycle(x12), O.filter_data(x12), rtol=0, atol=2e-6)
+
+
+@pytest.mark.parametrize("case", range(4))
+def test_regrid_vs_oracle(F, case):
+    from test_abi_and_host import GRID_CASES
+    lat, lon, tlat, tlon = GRID_CASES[case]
+    rng = np.random.default_rng(10 + case)
+    data = rng.normal(size=(3, 2, len(lat), len(lon))).astype(np.float32)
+    ref = O.regrid_lat_lon(data, lat, lon, tlat, tlon)
+    out = F.regrid_arrays(data, lat, lon, tlat, tlon)
+    assert out.shape == ref.shape and out.dtype == np.float32
+    np.testing.assert_allclose(out, ref, rtol=0, atol=5e-7)
+
+
+def test_regrid_identity_and_pole_rows(F):
+    lat, lon = np.linspace(-88, 88, 45), np.arange(0.0, 360, 4.0)
+    rng = np.random.default_rng(12)
+    data = rng.normal(size=(2, len(lat), len(lon))).astype(np.float32)
+    same = F.regrid_arrays(data, lat, lon, lat, lon)
+    np.testing.assert_allclose(same, data, rtol=0, atol=1e-6)                      # identical grids -> identity
+    poles = F.regrid_arrays(data, lat, lon, np.array([-90.0, 90.0]), lon)
+    np.testing.assert_allclose(poles[:, 0], np.repeat(data[:, 0].mean(-1, keepdims=True), len(lon), -1), atol=1e-6)
+    np.testing.assert_allclose(poles[:, 1], np.repeat(data[:, -1].mean(-1, keepdims=True), len(lon), -1), atol=1e-6)

@@ -42,3 +42,156 @@ def test_speculation_paths_agree(k_spec):
     errs = compare(res, ref)
     for name, e in errs.items():
         assert e <= TOL[name], (name, e, errs)
+
+
+def _apply(era, deltas, when=ERA_DATE, ignore_top=True, **kw):
+    eng = _engine(era, deltas)
+    return eng.apply(_dev(era), when, ignore_top_pressure_error=ignore_top, **kw), eng
+
+
+def _check(res, ref):
+    assert res["n_iter"] == ref["n_iter"], (res["phi_max_errors"], ref["phi_max_errors"])
+    errs = compare(res, ref)
+    for name, e in errs.items():
+        assert e <= TOL[name], (name, e, errs)
+    return errs
+
+
+def test_config1_european_domain():
+    """BASELINE configs[0]: 201x281 European subdomain, 137 levels, plev19, one timestep."""
+    era, deltas = make_case(201, 281, 1)
+    ref = run_oracle(era, deltas)
+    res, _ = _apply(era, deltas)
+    _check(res, ref)
+    # iteration-count margin of this seed: |E_N - thresh| must dwarf the fp32 storage noise
+    assert abs(ref["phi_max_errors"][-1] - 0.15) > 1e-3 * 0.15
+
+
+def test_config5_plev37_tight_threshold():
+    """BASELINE configs[4] (small grid): 37 pressure levels and thresh 1e-3 -> ~10 iterations."""
+    from pgw4era5_b200 import settings, synthetic as S
+    era, deltas = make_case(19, 47, 5, plev=S.PLEV37, region="GL")
+    ref = run_oracle(era, deltas, thresh_phi_ref_max_error=1e-3)
+    old = settings.thresh_phi_ref_max_error
+    settings.thresh_phi_ref_max_error = 1e-3
+    try:
+        res, _ = _apply(era, deltas)
+    finally:
+        settings.thresh_phi_ref_max_error = old
+    assert ref["n_iter"] >= 8
+    _check(res, ref)
+
+
+@pytest.mark.parametrize("when", ["2006-03-16T12", "2006-01-01T00", "2006-12-31T18", "2008-02-29T06"])
+def test_time_interpolation_cases(when):
+    """exact hit on a delta stamp, the two year wraps, and a leap day (functions.py:242-292)."""
+    from datetime import datetime
+    when = datetime.fromisoformat(when)
+    era, deltas = make_case(9, 33, 7)
+    ref = run_oracle(era, deltas, when=when)
+    res, _ = _apply(era, deltas, when=when)
+    _check(res, ref)
+
+
+def test_zero_deltas_identity():
+    era, deltas = make_case(12, 40, 21)
+    for v in deltas.values():
+        v["data"].zero_()
+    deltas["ps_hist"]["data"] += era["PS"]
+    res, _ = _apply(era, deltas)
+    assert res["n_iter"] == 1
+    for name in ("T", "U", "V", "PS", "T_SKIN", "T_SO"):
+        assert torch.equal(res[name].cpu().reshape(-1), era[name].reshape(-1)), name
+    assert float(res["delta_ps"].abs().max()) == 0.0
+    q = res["QV"].cpu().reshape(-1).double(); q0 = era["QV"].reshape(-1).double()
+    assert float(((q - q0).abs() / q0).max()) < 5e-6                    # rh -> q round trip in fp32
+
+
+def test_nan_handling_matches_oracle():
+    """NaN sea ice over land and NaN tos pass through exactly like the reference
+    (np.clip keeps NaN, integrate_tos masks them, step_03:103-125)."""
+    era, deltas = make_case(10, 36, 9, region="GL")
+    assert torch.isnan(era["FR_SEA_ICE"]).any() and torch.isnan(deltas["tos"]["data"]).any()
+    ref = run_oracle(era, deltas)
+    res, _ = _apply(era, deltas)
+    _check(res, ref)
+
+
+def test_errors_match_reference():
+    from pgw4era5_b200 import settings
+    era, deltas = make_case(8, 33, 23)
+    with pytest.raises(ValueError, match="top pressure"):                  # functions.py:417-425
+        _apply(era, deltas, ignore_top=False)
+    old = settings.max_n_iter
+    settings.max_n_iter = 3
+    try:
+        with pytest.raises(ValueError, match="did not converge"):           # step_03:315-319
+            _apply(era, deltas)
+    finally:
+        settings.max_n_iter = old
+    old = settings.p_ref_inp
+    settings.p_ref_inp = 100000
+    try:
+        with pytest.raises(ValueError, match="below the surface"):          # functions.py:162-165
+            _apply(era, deltas)
+    finally:
+        settings.p_ref_inp = old
+    bad = {k: dict(v) for k, v in deltas.items()}
+    bad["ps_hist"] = dict(deltas["ps_hist"], data=deltas["ps_hist"]["data"] * 0 + 50.0)
+    with pytest.raises(ValueError):                                         # functions.py:360-361
+        _apply(era, bad)
+    old = settings.p_ref_inp
+    settings.p_ref_inp = 31000
+    try:
+        with pytest.raises(KeyError):                                       # .sel(plev=p_ref), step_03:294
+            _apply(era, deltas)
+    finally:
+        settings.p_ref_inp = old
+
+
+def test_ps_bound_rerun():
+    """A stash sized for a too small ps bound is detected on the device and the step is rerun."""
+    era, deltas = make_case(8, 33, 2)
+    ref = run_oracle(era, deltas)
+    from pgw4era5_b200.engine import DeltaSet, PGWEngine
+    eng = PGWEngine(era["ak"], era["bk"], DeltaSet(deltas, device="cuda"), soil1=era["soil1"], ps_bound=60000.0)
+    res = eng.apply(_dev(era), ERA_DATE, ignore_top_pressure_error=True)
+    assert eng.stats["reruns"] >= 1 and eng.ps_bound > 100000
+    _check(res, ref)
+
+
+def test_global_size_properties():
+    """BASELINE configs[1] at full size (721x1440x137): properties that need no oracle run.
+    (a) zero deltas: one iteration, T/U/V/PS bit-identical; (b) the fused pass agrees with the
+    stand-alone operators on a latitude band; (c) result is independent of k_spec."""
+    from pgw4era5_b200 import synthetic as S
+    from pgw4era5_b200.engine import DeltaSet, PGWEngine
+    ny, nx = 721, 1440
+    era = S.make_era5(ny, nx, 2, device="cuda", orog_seed=2)
+    deltas = S.make_deltas(era, 2, device="cuda")
+    eng = PGWEngine(era["ak"], era["bk"], DeltaSet(deltas, device="cuda"), soil1=era["soil1"])
+    r1 = eng.apply(era, ERA_DATE, ignore_top_pressure_error=True)
+    n1 = r1["n_iter"]
+    ps1, q1 = r1["PS"].clone(), r1["QV"].clone()
+    r2 = eng.apply(era, ERA_DATE, ignore_top_pressure_error=True, k_spec=n1 + 3)      # rewrite path
+    assert r2["n_iter"] == n1
+    assert float((r2["PS"] - ps1).abs().max()) <= 1e-2
+    assert float((r2["QV"] - q1).abs().max()) <= 1e-7
+    assert 4 <= n1 <= 10 and r1["phi_max_errors"][-1] <= 0.15 < r1["phi_max_errors"][-2]
+    # band check against the oracle (rows 300..303)
+    band = slice(300, 304)
+    sub = {k: (v[..., band, :].cpu() if isinstance(v, torch.Tensor) and v.dim() >= 3 else v) for k, v in era.items()}
+    subd = {k: dict(v, data=v["data"][..., band, :].cpu()) for k, v in deltas.items()}
+    ref = run_oracle(sub, subd)
+    for name, tol in (("T", 1e-4), ("U", 1e-4), ("V", 1e-4)):
+        g = r1[name][..., band, :].cpu().numpy().astype(np.float64)
+        assert np.max(np.abs(g - ref[name])) <= tol, name
+    # zero deltas
+    for v in deltas.values():
+        v["data"].zero_()
+    deltas["ps_hist"]["data"] += era["PS"]
+    eng0 = PGWEngine(era["ak"], era["bk"], DeltaSet(deltas, device="cuda"), soil1=era["soil1"])
+    r0 = eng0.apply(era, ERA_DATE, ignore_top_pressure_error=True)
+    assert r0["n_iter"] == 1
+    for name in ("T", "U", "V", "PS"):
+        assert torch.equal(r0[name].reshape(-1), era[name].reshape(-1)), name
