@@ -305,9 +305,9 @@ def run_ours(a):
         from oracle import build as ob
         ob.build()
         _cpu_sample((1, 2, 64))
-        v, wall, cols = cpu_arm(6, 1, rows=8)
+        v, wall, cols = cpu_arm(12, 1, rows=8)
         cpu = {"value": v, "unit": "timesteps/s", "cores": 1, "kind": "port",
-               "sample": "6 bands of 8x1440 columns (%d columns = %.4f of one global timestep), fp64 oracle "
+               "sample": "12 bands of 8x1440 columns (%d columns = %.4f of one global timestep), fp64 oracle "
                          "port on 1 host core, %.1f s" % (cols, cols / 1038240.0, wall)}
 
     if rank == 0:
@@ -319,7 +319,8 @@ def run_ours(a):
                                    "(BASELINE configs[1]); N>1: timesteps sharded by rank (configs[2])" % (ny, nx),
                        "grid": a.grid, "ring": a.ring,
                        "l2": "inputs cycle through %d distinct 2.3 GB timesteps (>> 126 MB L2)" % a.ring,
-                       "parallelism": "timestep-sharded x%d" % world, "n_iter": n_iters,
+                       "parallelism": "timestep-sharded x%d" % world,
+                       "n_iter": {"min": int(min(n_iters)), "max": int(max(n_iters)), "steps": len(n_iters)},
                        "engine": dict(eng.stats), "broadcast_ms": bcast_ms},
             "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
             "clocks": sampler.summary(),

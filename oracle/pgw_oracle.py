@@ -534,7 +534,7 @@ def regrid_lat_lon(data, lat_gcm, lon_gcm, targ_lat, targ_lon):
 # ---------------------------------------------------------------------------
 def pgw_for_era5(era, deltas, era_step_dt, *, p_ref_inp=30000, adj_factor=0.95,
                  thresh_phi_ref_max_error=0.15, max_n_iter=20,
-                 ignore_top_pressure_error=False):
+                 ignore_top_pressure_error=False, n_iter_fixed=None):
     """
     step_03_apply_to_era.py:44-381 with i_reinterp=0 and a scalar p_ref.
 
@@ -545,6 +545,11 @@ def pgw_for_era5(era, deltas, era_step_dt, *, p_ref_inp=30000, adj_factor=0.95,
             tas,hurs,ts,tos,siconc (2-D) and 'ps_hist' (HIST ps, 2-D).
     Returns dict with PS,T,QV,U,V,T_SKIN,T_SO,FR_SEA_ICE (float64), 'n_iter',
     'phi_max_errors' (one per iteration) and 'deltas' (interpolate_full taps).
+
+    n_iter_fixed (test hook, not in the reference): run exactly that many iterations
+    regardless of the threshold and also return 'ps_traj' (ps after each iteration's
+    update); used to check the latitude-band scheme in which the stopping rule is
+    evaluated on the MAX over all bands.
     """
     f64 = lambda a: np.asarray(a, dtype=np.float64)
     ak, bk = f64(era["ak"]), f64(era["bk"])
@@ -598,7 +603,9 @@ def pgw_for_era5(era, deltas, era_step_dt, *, p_ref_inp=30000, adj_factor=0.95,
     errs = []
     it = 1
     plev_zg = f64(deltas["zg"]["plev"])
-    while phi_ref_max_error > thresh_phi_ref_max_error:
+    ps_traj, hus_traj = [], []
+    while (phi_ref_max_error > thresh_phi_ref_max_error if n_iter_fixed is None
+           else it <= n_iter_fixed):
         delta_ps = delta_ps + adj_ps
         ps_pgw = PS + delta_ps
         pa_pgw = lev(akm) + ps_pgw[:, None] * lev(bkm)
@@ -621,11 +628,14 @@ def pgw_for_era5(era, deltas, era_step_dt, *, p_ref_inp=30000, adj_factor=0.95,
             phi_ref_max_error = (np.nanmax(np.abs(phi_ref_error))
                                  if not np.all(np.isnan(phi_ref_error)) else np.nan)
         errs.append(float(phi_ref_max_error))
+        if n_iter_fixed is not None:
+            ps_traj.append(ps_pgw.copy())
+            hus_traj.append(vars_pgw["hus"].copy())
         it += 1
-        if it > max_n_iter:
+        if n_iter_fixed is None and it > max_n_iter:
             raise ValueError("ERROR! Pressure adjustment did not converge")
     out_deltas["ps"] = ps_pgw - PS
     return dict(PS=ps_pgw, T=vars_pgw["ta"], QV=vars_pgw["hus"], U=vars_pgw["ua"],
                 V=vars_pgw["va"], T_SKIN=T_SKIN, T_SO=T_SO, FR_SEA_ICE=sic,
                 n_iter=it - 1, phi_max_errors=errs, deltas=out_deltas,
-                RELHUM_era=RELHUM)
+                RELHUM_era=RELHUM, ps_traj=ps_traj, hus_traj=hus_traj)
