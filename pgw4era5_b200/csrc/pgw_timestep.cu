@@ -145,9 +145,11 @@ pgw_column_kernel(const __grid_constant__ pgw_timestep_args a, const int lst, co
     int slot_w = 0;                                  // slot the next prefetch writes
     uint32_t off_w = (uint32_t)(L - 1) * n + c;      // element offset of the next prefetched level
     int lev_w = L - 1;
-    auto prefetch = [&]() {
+    // `zero` is 0, but computed from values just read out of the slot about to be overwritten
+    // (pair loops): it makes the async copy wait for those shared-memory reads.
+    auto prefetch = [&](int zero = 0) {
         if (lev_w >= 0) {
-            float *dst = my_ring + slot_w * (4 * NT);
+            float *dst = my_ring + slot_w * (4 * NT) + zero;
             __pipeline_memcpy_async(dst, gT + off_w, 4);
             __pipeline_memcpy_async(dst + NT, gQ + off_w, 4);
             __pipeline_memcpy_async(dst + 2 * NT, gU + off_w, 4);
@@ -265,9 +267,20 @@ pgw_column_kernel(const __grid_constant__ pgw_timestep_args a, const int lst, co
     if (!era_open) errbits |= PGW_ERR_PREF_BELOW_SFC;
     float psn_f = ps_f;                             // ps used for QV; replaced after the iteration
 
-    // One model level: deltas at p, RH of the ERA state, PGW state, outputs T/U/V.
-    auto level = [&](const float2 m, uint32_t off, float t, float q, float u, float v, float &dta_out, float &e_pgw) {
-        const float p = fmaf(ps_f, m.y, m.x);
+    auto read_fence = [](float x0, float x1, float x2, float x3) {
+        int z;
+        asm volatile("{\n\t.reg .b32 t;\n\tor.b32 t, %1, %2;\n\tor.b32 t, t, %3;\n\tor.b32 t, t, %4;\n\t"
+                     "and.b32 %0, t, 0;\n\t}"
+                     : "=r"(z) : "r"(__float_as_int(x0)), "r"(__float_as_int(x1)), "r"(__float_as_int(x2)),
+                       "r"(__float_as_int(x3)));
+        return z;
+    };
+    // The per-level work is split into the (sequential, cheap) walker step and the (independent,
+    // expensive) thermodynamics.  The sweeps process levels in PAIRS: both walker steps first,
+    // then the thermodynamics of the two levels in one branch-free block so that the two
+    // dependency chains interleave (the kernel is issue-latency bound, not DRAM bound).
+    struct Dlt { float ta, hur, ua, va; };
+    auto walk = [&](float p) {
         if (fmaxf(wA.p_lo, wB.p_lo) > p) {
             advance(wA, p, v_ta, v_hur);
             advance(wB, p, v_ua, v_va);
@@ -276,50 +289,46 @@ pgw_column_kernel(const __grid_constant__ pgw_timestep_args a, const int lst, co
         const float l2a = (wA.inv_p_lo == wB.inv_p_lo) ? l2b : fast_lg2(p * wA.inv_p_lo);
         const float tA = l2a * wA.inv_w, tB = l2b * wB.inv_w;
         // t == 0: exact node hit or constant extrapolation -> the node value itself (NaN-safe)
-        const float dta = (tA == 0.0f) ? wA.a_lo : fmaf(tA, wA.a_d, wA.a_lo);
-        const float dhur = (tA == 0.0f) ? wA.b_lo : fmaf(tA, wA.b_d, wA.b_lo);
-        const float dua = (tB == 0.0f) ? wB.a_lo : fmaf(tB, wB.a_d, wB.a_lo);
-        const float dva = (tB == 0.0f) ? wB.b_lo : fmaf(tB, wB.b_d, wB.b_lo);
-
-        // saturation vapour pressure of the ERA and the PGW state (functions.py:74-105);
-        // T - 273.16 is formed from the exact T - 273 so that T_pgw is never rounded to fp32
+        Dlt d;
+        d.ta = (tA == 0.0f) ? wA.a_lo : fmaf(tA, wA.a_d, wA.a_lo);
+        d.hur = (tA == 0.0f) ? wA.b_lo : fmaf(tA, wA.b_d, wA.b_lo);
+        d.ua = (tB == 0.0f) ? wB.a_lo : fmaf(tB, wB.a_d, wB.a_lo);
+        d.va = (tB == 0.0f) ? wB.b_lo : fmaf(tB, wB.b_d, wB.b_lo);
+        return d;
+    };
+    // Saturation vapour pressure of the ERA and the PGW state (functions.py:74-105), RELHUM of
+    // the ERA state (:107-116) + delta, back to vapour pressure (:123); T - 273.16 is formed from
+    // the exact T - 273 so that T_pgw is never rounded to fp32.  `cold` (warp-uniform): every
+    // temperature involved is <= 250.16 K, ice only (alpha == 0 exactly).  The general form is
+    // branch free: both exponentials, alpha from selects (exactly 1 / 0 outside the mixed band).
+    auto thermo = [&](bool cold, float p, float t, float q, const Dlt &d) -> float {
         const float tm273 = t - 273.0f;
-        const float dTe = tm273 - 0.16f, tkp = tm273 + dta, dTp = tm273 + (dta - 0.16f);
+        const float dTe = tm273 - 0.16f, tkp = tm273 + d.ta, dTp = tm273 + (d.ta - 0.16f);
+        constexpr float kCw = 17.502f * 1.4426950408889634f, kCi = 22.587f * 1.4426950408889634f;
         float es_e, es_p;
-        if (fmaxf(dTe, dTp) <= -23.0f) {
-            // both states at or below 250.16 K (most of the column): ice only, alpha == 0 exactly
+        if (cold) {
             const float de = tm273 + (273.0f + 0.7f), dp = tkp + (273.0f + 0.7f);
             const float rr = fast_rcp(de * dp);               // one reciprocal for both states
-            es_e = 611.21f * fast_ex2((22.587f * 1.4426950408889634f) * dTe * (rr * dp));
-            es_p = 611.21f * fast_ex2((22.587f * 1.4426950408889634f) * dTp * (rr * de));
+            es_e = 611.21f * fast_ex2(kCi * dTe * (rr * dp));
+            es_p = 611.21f * fast_ex2(kCi * dTp * (rr * de));
         } else {
-            const bool we = dTe >= 0.0f, wp = dTp >= 0.0f;
-            const float ce = we ? (273.0f - 32.19f) : (273.0f + 0.7f), cp = wp ? (273.0f - 32.19f) : (273.0f + 0.7f);
-            const float ae = we ? (17.502f * 1.4426950408889634f) : (22.587f * 1.4426950408889634f);
-            const float ap = wp ? (17.502f * 1.4426950408889634f) : (22.587f * 1.4426950408889634f);
-            const float de = tm273 + ce, dp = tkp + cp;
-            const float rr = fast_rcp(de * dp);
-            es_e = 611.21f * fast_ex2(ae * dTe * (rr * dp));
-            es_p = 611.21f * fast_ex2(ap * dTp * (rr * de));
-            if (!(dTe >= 0.0f || dTe <= -23.0f)) {            // mixed phase (or NaN): blend water/ice
-                const float ew = 611.21f * __expf(__fdividef(17.502f * dTe, tm273 + (273.0f - 32.19f)));
-                const float r = (dTe + 23.0f) * (1.0f / 23.0f), al = r * r;
-                es_e = al * ew + (1.0f - al) * es_e;
-            }
-            if (!(dTp >= 0.0f || dTp <= -23.0f)) {
-                const float ew = 611.21f * __expf(__fdividef(17.502f * dTp, tkp + (273.0f - 32.19f)));
-                const float r = (dTp + 23.0f) * (1.0f / 23.0f), al = r * r;
-                es_p = al * ew + (1.0f - al) * es_p;
-            }
+            const float dew = tm273 + (273.0f - 32.19f), dei = tm273 + (273.0f + 0.7f);
+            const float dpw = tkp + (273.0f - 32.19f), dpi = tkp + (273.0f + 0.7f);
+            const float pe = dew * dei, pp = dpw * dpi;
+            const float rr = fast_rcp(pe * pp);               // one reciprocal for all four quotients
+            const float re = rr * pp, rp = rr * pe;           // 1/pe, 1/pp
+            const float ew_e = fast_ex2(kCw * dTe * (re * dei)), ei_e = fast_ex2(kCi * dTe * (re * dew));
+            const float ew_p = fast_ex2(kCw * dTp * (rp * dpi)), ei_p = fast_ex2(kCi * dTp * (rp * dpw));
+            const float r_e = (dTe + 23.0f) * (1.0f / 23.0f), r_p = (dTp + 23.0f) * (1.0f / 23.0f);
+            const float al_e = dTe >= 0.0f ? 1.0f : (dTe <= -23.0f ? 0.0f : r_e * r_e);   // NaN stays NaN
+            const float al_p = dTp >= 0.0f ? 1.0f : (dTp <= -23.0f ? 0.0f : r_p * r_p);
+            es_e = 611.21f * (al_e * ew_e + (1.0f - al_e) * ei_e);
+            es_p = 611.21f * (al_p * ew_p + (1.0f - al_p) * ei_p);
         }
-        // RELHUM of the ERA state (functions.py:107-116) + delta, back to vapour pressure (:123)
-        const float rh_pgw = fmaf(100.0f * q * p, fast_rcp((0.622f + 0.378f * q) * es_e), dhur);
-        e_pgw = rh_pgw * 0.01f * es_p;
-        dta_out = dta;
-        st_stream(oT + off, t + dta);     // == (float)((double)t + (double)dta)
-        st_stream(oU + off, u + dua);
-        st_stream(oV + off, v + dva);
+        const float rh_pgw = fmaf(100.0f * q * p, fast_rcp((0.622f + 0.378f * q) * es_e), d.hur);
+        return rh_pgw * 0.01f * es_p;
     };
+    auto is_cold = [](float t, float dta) { return fmaxf(t, t + dta) <= 250.0f; };   // conservative
 
     // ---------------- phase 1: surface .. p_ref, parked in shared memory ----------------
     uint32_t off = (uint32_t)(L - 1) * n + c;
@@ -329,30 +338,61 @@ pgw_column_kernel(const __grid_constant__ pgw_timestep_args a, const int lst, co
     double acc_res = 0.0, t_low_d = 0.0;
     {
         float2 *pTe = st_Te + (size_t)(L - 1 - lst) * NT + tid;
-        for (int l = L - 1; l >= lst; --l, off -= n, pTe -= NT) {
-            __pipeline_wait_prior(kRing - 1);
-            const float *slot = my_ring + slot_r * (4 * NT);
-            const float t = slot[0], q = slot[NT], u = slot[2 * NT], v = slot[3 * NT];
-            const float2 m = s_m[l];
-            slot_r = (slot_r == kRing) ? 0 : slot_r + 1;
-            prefetch();
-            float dta, e_pgw;
-            level(m, off, t, q, u, v, dta, e_pgw);
-            const double td = (double)t;
-            const float t_pgw = t + dta;
-            *pTe = make_float2(t_pgw, e_pgw);
-            if (l == L - 1) t_low_d = td + (double)dta;
-            // geopotential of the ERA state (functions.py:128-189)
+        // ERA geopotential of one layer (functions.py:128-189), sequential in the column
+        auto era_layer = [&](int l, float t, float q, float dta, float t_pgw) {
             if (era_open) {
                 const double2 hl = s_hl[l];
                 double pt = fma(PSd, hl.y, hl.x);
                 if (pt < pref) { pt = pref; era_open = false; }     // layer that contains p_ref (:174-179)
+                const double td = (double)t;
                 const double tv = fma(td, 0.61 * (double)q, td);
                 const double dl = ln_ratio<FAST>(pb_era, pt, lk);
                 acc_era = fma(tv, dl, acc_era);
                 acc_res = fma((td + (double)dta) - (double)t_pgw, dl, acc_res);
                 pb_era = pt;
             }
+        };
+        int l = L - 1;
+        for (; l - 1 >= lst; l -= 2, off -= 2 * n, pTe -= 2 * NT) {
+            __pipeline_wait_prior(kRing - 2);
+            const float *sl0 = my_ring + slot_r * (4 * NT);
+            const float t0 = sl0[0], q0 = sl0[NT], u0 = sl0[2 * NT], v0 = sl0[3 * NT];
+            slot_r = (slot_r == kRing) ? 0 : slot_r + 1;
+            const float *sl1 = my_ring + slot_r * (4 * NT);
+            const float t1 = sl1[0], q1 = sl1[NT], u1 = sl1[2 * NT], v1 = sl1[3 * NT];
+            slot_r = (slot_r == kRing) ? 0 : slot_r + 1;
+            const float2 m0 = s_m[l], m1 = s_m[l - 1];
+            prefetch(); prefetch(read_fence(t0, q0, u0, v0));   // 2nd copy reuses the slot of level l
+            const float p0 = fmaf(ps_f, m0.y, m0.x), p1 = fmaf(ps_f, m1.y, m1.x);
+            const Dlt d0 = walk(p0);
+            const Dlt d1 = walk(p1);
+            const bool cold = __all_sync(0xffffffffu, is_cold(t0, d0.ta) && is_cold(t1, d1.ta));
+            const float e0 = thermo(cold, p0, t0, q0, d0), e1 = thermo(cold, p1, t1, q1, d1);
+            const float tp0 = t0 + d0.ta, tp1 = t1 + d1.ta;   // == (float)((double)t + (double)dta)
+            st_stream(oT + off, tp0); st_stream(oU + off, u0 + d0.ua); st_stream(oV + off, v0 + d0.va);
+            st_stream(oT + off - n, tp1); st_stream(oU + off - n, u1 + d1.ua); st_stream(oV + off - n, v1 + d1.va);
+            pTe[0] = make_float2(tp0, e0);
+            pTe[-NT] = make_float2(tp1, e1);
+            if (l == L - 1) t_low_d = (double)t0 + (double)d0.ta;
+            era_layer(l, t0, q0, d0.ta, tp0);
+            era_layer(l - 1, t1, q1, d1.ta, tp1);
+        }
+        if (l >= lst) {                                   // odd number of parked levels
+            __pipeline_wait_prior(kRing - 1);
+            const float *sl0 = my_ring + slot_r * (4 * NT);
+            const float t0 = sl0[0], q0 = sl0[NT], u0 = sl0[2 * NT], v0 = sl0[3 * NT];
+            slot_r = (slot_r == kRing) ? 0 : slot_r + 1;
+            const float2 m0 = s_m[l];
+            prefetch();
+            const float p0 = fmaf(ps_f, m0.y, m0.x);
+            const Dlt d0 = walk(p0);
+            const float e0 = thermo(false, p0, t0, q0, d0);
+            const float tp0 = t0 + d0.ta;
+            st_stream(oT + off, tp0); st_stream(oU + off, u0 + d0.ua); st_stream(oV + off, v0 + d0.va);
+            pTe[0] = make_float2(tp0, e0);
+            if (l == L - 1) t_low_d = (double)t0 + (double)d0.ta;
+            era_layer(l, t0, q0, d0.ta, tp0);
+            off -= n;
         }
     }
     const double fis = (double)r_fis;
@@ -425,16 +465,45 @@ pgw_column_kernel(const __grid_constant__ pgw_timestep_args a, const int lst, co
             st_stream(oQ + o2, 0.622f * e * fast_rcp(fmaf(-0.378f, e, fmaf(psn_f, m.y, m.x))));
         }
     }
-    for (int l = lst - 1; l >= 0; --l, off -= n) {
-        __pipeline_wait_prior(kRing - 1);
-        const float *slot = my_ring + slot_r * (4 * NT);
-        const float t = slot[0], q = slot[NT], u = slot[2 * NT], v = slot[3 * NT];
-        const float2 m = s_m[l];
-        slot_r = (slot_r == kRing) ? 0 : slot_r + 1;
-        prefetch();
-        float dta, e_pgw;
-        level(m, off, t, q, u, v, dta, e_pgw);
-        st_stream(oQ + off, 0.622f * e_pgw * fast_rcp(fmaf(-0.378f, e_pgw, fmaf(psn_f, m.y, m.x))));
+    {
+        auto qv_of = [&](float e, float2 m) {     // functions.py:66-72 with the adjusted ps
+            return 0.622f * e * fast_rcp(fmaf(-0.378f, e, fmaf(psn_f, m.y, m.x)));
+        };
+        int l = lst - 1;
+        for (; l - 1 >= 0; l -= 2, off -= 2 * n) {
+            __pipeline_wait_prior(kRing - 2);
+            const float *sl0 = my_ring + slot_r * (4 * NT);
+            const float t0 = sl0[0], q0 = sl0[NT], u0 = sl0[2 * NT], v0 = sl0[3 * NT];
+            slot_r = (slot_r == kRing) ? 0 : slot_r + 1;
+            const float *sl1 = my_ring + slot_r * (4 * NT);
+            const float t1 = sl1[0], q1 = sl1[NT], u1 = sl1[2 * NT], v1 = sl1[3 * NT];
+            slot_r = (slot_r == kRing) ? 0 : slot_r + 1;
+            const float2 m0 = s_m[l], m1 = s_m[l - 1];
+            prefetch(); prefetch(read_fence(t0, q0, u0, v0));
+            const float p0 = fmaf(ps_f, m0.y, m0.x), p1 = fmaf(ps_f, m1.y, m1.x);
+            const Dlt d0 = walk(p0);
+            const Dlt d1 = walk(p1);
+            const bool cold = __all_sync(0xffffffffu, is_cold(t0, d0.ta) && is_cold(t1, d1.ta));
+            const float e0 = thermo(cold, p0, t0, q0, d0), e1 = thermo(cold, p1, t1, q1, d1);
+            st_stream(oT + off, t0 + d0.ta); st_stream(oU + off, u0 + d0.ua); st_stream(oV + off, v0 + d0.va);
+            st_stream(oQ + off, qv_of(e0, m0));
+            st_stream(oT + off - n, t1 + d1.ta); st_stream(oU + off - n, u1 + d1.ua); st_stream(oV + off - n, v1 + d1.va);
+            st_stream(oQ + off - n, qv_of(e1, m1));
+        }
+        if (l >= 0) {
+            __pipeline_wait_prior(kRing - 1);
+            const float *sl0 = my_ring + slot_r * (4 * NT);
+            const float t0 = sl0[0], q0 = sl0[NT], u0 = sl0[2 * NT], v0 = sl0[3 * NT];
+            slot_r = (slot_r == kRing) ? 0 : slot_r + 1;
+            const float2 m0 = s_m[l];
+            prefetch();
+            const float p0 = fmaf(ps_f, m0.y, m0.x);
+            const Dlt d0 = walk(p0);
+            const float e0 = thermo(false, p0, t0, q0, d0);
+            st_stream(oT + off, t0 + d0.ta); st_stream(oU + off, u0 + d0.ua); st_stream(oV + off, v0 + d0.va);
+            st_stream(oQ + off, qv_of(e0, m0));
+            off -= n;
+        }
     }
     __pipeline_wait_prior(0);
 

@@ -166,6 +166,7 @@ class PGWEngine:
         self.ps_bound = float(ps_bound)
         self.group = group
         self.k_pred = 8
+        self._n_hist = []               # iteration counts of the last few timesteps
         self._ws = {}
         self.stats = dict(timesteps=0, rewrites=0, reruns=0, launches=0)
         self.kernel_events = None       # set to [] to collect CUDA events around the column kernel
@@ -327,7 +328,10 @@ class PGWEngine:
             self.stats["reruns"] += 1
             return self.submit(ctx["era"], ctx["when"], out=p.out, ignore_top_pressure_error=ctx["ignore_top"],
                                k_spec=ctx["k_max"], file_name=ctx["file_name"], slot=ctx["slot"]).result()
-        self.k_pred = int(n_iter)
+        # predict the largest recent count: one iteration too many costs a cheap rewrite
+        # (+13 % traffic), one too few a full rerun
+        self._n_hist = (self._n_hist + [int(n_iter)])[-4:]
+        self.k_pred = max(self._n_hist)
         self.stats["timesteps"] += 1
         self.stats["rewrites"] += int(rewritten)
         res = dict(p.out)
