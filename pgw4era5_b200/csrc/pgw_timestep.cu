@@ -101,6 +101,7 @@ struct Walk2 {
 struct Tslab32 { const float *lo, *hi; float w; };
 
 constexpr int kRing = 5;     // levels in flight per thread (cp.async ring, +1 spare slot)
+constexpr int kL2Ahead = 6;  // delta nodes pulled into L2 this many advances ahead of their use
 
 template <int NT, bool FAST>
 __global__ void __launch_bounds__(NT, 3)
@@ -204,6 +205,16 @@ pgw_column_kernel(const __grid_constant__ pgw_timestep_args a, const int lst, co
         b0 = __ldg(vb.lo + off); b1 = __ldg(vb.hi + off);
     };
     auto blend = [](float w, float x0, float x1) { return (w == 0.0f) ? x0 : fmaf(w, x1 - x0, x0); };
+    // The register prefetch above covers two advances (~2 levels of work), less than a DRAM
+    // round trip under load; the lines of node j are therefore pulled into L2 kL2Ahead
+    // advances ahead, which costs neither registers nor shared memory.
+    auto l2_prefetch = [&](const Tslab32 &va, const Tslab32 &vb, int j) {
+        const uint32_t off = (uint32_t)(desc ? (K - 1 - j) : j) * n + c;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(va.lo + off));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(va.hi + off));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(vb.lo + off));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(vb.hi + off));
+    };
 
     Walk2 wA, wB;
     {
@@ -233,27 +244,57 @@ pgw_column_kernel(const __grid_constant__ pgw_timestep_args a, const int lst, co
         load_raw(v_ua, v_va, K - 2, wB.a_n0, wB.a_n1, wB.b_n0, wB.b_n1);
         wB.a_m0 = wB.a_m1 = wB.b_m0 = wB.b_m1 = 0.0f;
         if (K >= 3) load_raw(v_ua, v_va, K - 3, wB.a_m0, wB.a_m1, wB.b_m0, wB.b_m1);
+#pragma unroll
+        for (int d = 3; d <= kL2Ahead; ++d) {
+            if (s - d >= 0) l2_prefetch(v_ta, v_hur, s - d);
+            if (K - 1 - d >= 0) l2_prefetch(v_ua, v_va, K - 1 - d);
+        }
     }
     float min_src_p = (wA.lo == 0) ? wA.p_lo : s_plev[0];
 
-    // advance a walker until p_lo <= p (or the first node has been passed)
-    auto advance = [&](Walk2 &w, float p, const Tslab32 &va, const Tslab32 &vb) {
-        while (w.p_lo > p) {
-            const float hi_p = w.p_lo, hi_a = w.a_lo, hi_b = w.b_lo;
-            const bool from_synth = (hi_p != s_plev[w.lo]);     // leaving the (ps_hist, sfc) node
-            --w.lo;
-            if (w.lo >= 0) {
-                w.p_lo = s_plev[w.lo]; w.inv_p_lo = s_inv_plev[w.lo];
-                w.a_lo = blend(va.w, w.a_n0, w.a_n1); w.b_lo = blend(vb.w, w.b_n0, w.b_n1);
-                w.a_d = hi_a - w.a_lo; w.b_d = hi_b - w.b_lo;
-                w.inv_w = from_synth ? fast_rcp(fast_lg2(hi_p * w.inv_p_lo)) : s_inv_w[w.lo];
-                w.a_n0 = w.a_m0; w.a_n1 = w.a_m1; w.b_n0 = w.b_m0; w.b_n1 = w.b_m1;
-                if (w.lo >= 2) load_raw(va, vb, w.lo - 2, w.a_m0, w.a_m1, w.b_m0, w.b_m1);
-            } else {
-                // above node 0: constant extrapolation with node 0's values; p_lo = 0 ends the walk
-                w.a_d = 0.0f; w.b_d = 0.0f; w.inv_w = 0.0f; w.p_lo = 0.0f; w.inv_p_lo = 1.0f;
-            }
+    // One downward step of a walker, split in two so that the steps of both walkers can be
+    // ordered "consume, consume, load, load": the prefetched registers of a walker are read
+    // (which waits for loads issued one step, i.e. several levels, ago) before ANY new load is
+    // issued.  Issued the other way round, the second walker's register reads wait on the
+    // scoreboard of the first walker's brand-new loads: a full DRAM round trip per step.
+    auto step_consume = [&](Walk2 &w, const Tslab32 &va, const Tslab32 &vb) {
+        const float hi_p = w.p_lo, hi_a = w.a_lo, hi_b = w.b_lo;
+        const bool from_synth = (hi_p != s_plev[w.lo]);     // leaving the (ps_hist, sfc) node
+        --w.lo;
+        if (w.lo >= 0) {
+            w.p_lo = s_plev[w.lo]; w.inv_p_lo = s_inv_plev[w.lo];
+            w.a_lo = blend(va.w, w.a_n0, w.a_n1); w.b_lo = blend(vb.w, w.b_n0, w.b_n1);
+            w.a_d = hi_a - w.a_lo; w.b_d = hi_b - w.b_lo;
+            w.inv_w = from_synth ? fast_rcp(fast_lg2(hi_p * w.inv_p_lo)) : s_inv_w[w.lo];
+            w.a_n0 = w.a_m0; w.a_n1 = w.a_m1; w.b_n0 = w.b_m0; w.b_n1 = w.b_m1;
+        } else {
+            // above node 0: constant extrapolation with node 0's values; p_lo = 0 ends the walk
+            w.a_d = 0.0f; w.b_d = 0.0f; w.inv_w = 0.0f; w.p_lo = 0.0f; w.inv_p_lo = 1.0f;
         }
+    };
+    // `zero` (== 0) carries a data dependency on the registers consumed above
+    auto step_load = [&](Walk2 &w, const Tslab32 &va, const Tslab32 &vb, int zero) {
+        if (w.lo >= 2) load_raw(va, vb, w.lo - 2 + zero, w.a_m0, w.a_m1, w.b_m0, w.b_m1);
+        if (w.lo >= kL2Ahead) l2_prefetch(va, vb, w.lo - kL2Ahead);
+    };
+    auto reg_fence = [](float x0, float x1, float x2, float x3) {
+        int z;
+        asm volatile("{\n\t.reg .b32 t;\n\tor.b32 t, %1, %2;\n\tor.b32 t, t, %3;\n\tor.b32 t, t, %4;\n\t"
+                     "and.b32 %0, t, 0;\n\t}"
+                     : "=r"(z) : "r"(__float_as_int(x0)), "r"(__float_as_int(x1)), "r"(__float_as_int(x2)),
+                       "r"(__float_as_int(x3)));
+        return z;
+    };
+    // advance both walkers until p_lo <= p (or the first node has been passed)
+    auto advance = [&](float p) {
+        do {
+            const bool sa = wA.p_lo > p, sb = wB.p_lo > p;
+            if (sa) step_consume(wA, v_ta, v_hur);
+            if (sb) step_consume(wB, v_ua, v_va);
+            const int zero = reg_fence(wA.a_n1, wA.b_n1, wB.a_n1, wB.b_n1);
+            if (sa) step_load(wA, v_ta, v_hur, zero);
+            if (sb) step_load(wB, v_ua, v_va, zero);
+        } while (fmaxf(wA.p_lo, wB.p_lo) > p);
     };
 
     LnConst lk{2.0 / 3.0, 2.0 / 5.0, 2.0 / 7.0};
@@ -267,24 +308,14 @@ pgw_column_kernel(const __grid_constant__ pgw_timestep_args a, const int lst, co
     if (!era_open) errbits |= PGW_ERR_PREF_BELOW_SFC;
     float psn_f = ps_f;                             // ps used for QV; replaced after the iteration
 
-    auto read_fence = [](float x0, float x1, float x2, float x3) {
-        int z;
-        asm volatile("{\n\t.reg .b32 t;\n\tor.b32 t, %1, %2;\n\tor.b32 t, t, %3;\n\tor.b32 t, t, %4;\n\t"
-                     "and.b32 %0, t, 0;\n\t}"
-                     : "=r"(z) : "r"(__float_as_int(x0)), "r"(__float_as_int(x1)), "r"(__float_as_int(x2)),
-                       "r"(__float_as_int(x3)));
-        return z;
-    };
+    const auto read_fence = reg_fence;
     // The per-level work is split into the (sequential, cheap) walker step and the (independent,
     // expensive) thermodynamics.  The sweeps process levels in PAIRS: both walker steps first,
     // then the thermodynamics of the two levels in one branch-free block so that the two
     // dependency chains interleave (the kernel is issue-latency bound, not DRAM bound).
     struct Dlt { float ta, hur, ua, va; };
     auto walk = [&](float p) {
-        if (fmaxf(wA.p_lo, wB.p_lo) > p) {
-            advance(wA, p, v_ta, v_hur);
-            advance(wB, p, v_ua, v_va);
-        }
+        if (fmaxf(wA.p_lo, wB.p_lo) > p) advance(p);
         const float l2b = fast_lg2(p * wB.inv_p_lo);
         const float l2a = (wA.inv_p_lo == wB.inv_p_lo) ? l2b : fast_lg2(p * wA.inv_p_lo);
         const float tA = l2a * wA.inv_w, tB = l2b * wB.inv_w;
@@ -335,20 +366,25 @@ pgw_column_kernel(const __grid_constant__ pgw_timestep_args a, const int lst, co
     // T_pgw is parked as fp32.  Its rounding residual r_l (|r_l| <= 1.5e-5 K) enters the
     // geopotential as Rd * sum_l r_l dlnp_l; that sum is taken once with the ERA pressures
     // (its change over the iteration is < 1e-8 m2/s2) and added to every iteration's sum.
-    double acc_res = 0.0, t_low_d = 0.0;
+    double acc_res = 0.0, acc_pgw0 = 0.0, t_low_d = 0.0;
     {
         float2 *pTe = st_Te + (size_t)(L - 1 - lst) * NT + tid;
         // ERA geopotential of one layer (functions.py:128-189), sequential in the column
-        auto era_layer = [&](int l, float t, float q, float dta, float t_pgw) {
+        // The first iteration of the fixed point (dps = 0) integrates the PGW state over the
+        // same pressures, so its sum is taken here as well and phase 2 starts at iteration 1.
+        auto era_layer = [&](int l, float p, float t, float q, float dta, float t_pgw, float e_pgw) {
             if (era_open) {
                 const double2 hl = s_hl[l];
                 double pt = fma(PSd, hl.y, hl.x);
                 if (pt < pref) { pt = pref; era_open = false; }     // layer that contains p_ref (:174-179)
-                const double td = (double)t;
+                const double td = (double)t, tpd = (double)t_pgw;
                 const double tv = fma(td, 0.61 * (double)q, td);
+                const float g = fast_rcp(fmaf(-0.378f, e_pgw, p));
+                const double tvp = fma(tpd, (double)((0.61f * 0.622f) * e_pgw * g), tpd);
                 const double dl = ln_ratio<FAST>(pb_era, pt, lk);
                 acc_era = fma(tv, dl, acc_era);
-                acc_res = fma((td + (double)dta) - (double)t_pgw, dl, acc_res);
+                acc_pgw0 = fma(tvp, dl, acc_pgw0);
+                acc_res = fma((td + (double)dta) - tpd, dl, acc_res);
                 pb_era = pt;
             }
         };
@@ -374,8 +410,8 @@ pgw_column_kernel(const __grid_constant__ pgw_timestep_args a, const int lst, co
             pTe[0] = make_float2(tp0, e0);
             pTe[-NT] = make_float2(tp1, e1);
             if (l == L - 1) t_low_d = (double)t0 + (double)d0.ta;
-            era_layer(l, t0, q0, d0.ta, tp0);
-            era_layer(l - 1, t1, q1, d1.ta, tp1);
+            era_layer(l, p0, t0, q0, d0.ta, tp0, e0);
+            era_layer(l - 1, p1, t1, q1, d1.ta, tp1, e1);
         }
         if (l >= lst) {                                   // odd number of parked levels
             __pipeline_wait_prior(kRing - 1);
@@ -391,7 +427,7 @@ pgw_column_kernel(const __grid_constant__ pgw_timestep_args a, const int lst, co
             st_stream(oT + off, tp0); st_stream(oU + off, u0 + d0.ua); st_stream(oV + off, v0 + d0.va);
             pTe[0] = make_float2(tp0, e0);
             if (l == L - 1) t_low_d = (double)t0 + (double)d0.ta;
-            era_layer(l, t0, q0, d0.ta, tp0);
+            era_layer(l, p0, t0, q0, d0.ta, tp0, e0);
             off -= n;
         }
     }
@@ -414,10 +450,13 @@ pgw_column_kernel(const __grid_constant__ pgw_timestep_args a, const int lst, co
         if (psn > a.ps_bound) errbits |= PGW_ERR_PS_BOUND;
         double pb = fma(psn, hl_sfc.y, hl_sfc.x);
         if (pb < pref) errbits |= PGW_ERR_PREF_BELOW_SFC;
+        double acc = acc_res;
+        if (k == 0) {
+            acc += acc_pgw0;            // psn == PS: summed in phase 1 together with the ERA state
+        } else {
         // layers ltop..L-1 are entirely below p_ref for this ps; it moves by at most a level or two
         while (ltop > lst) { const double2 h = s_hl[ltop - 1]; if (fma(psn, h.y, h.x) >= pref) --ltop; else break; }
         while (ltop < L) { const double2 h = s_hl[ltop]; if (fma(psn, h.y, h.x) < pref) ++ltop; else break; }
-        double acc = acc_res;
         const float2 *pTe = bTe;
         int l = L - 1;
 #pragma unroll 4
@@ -442,6 +481,7 @@ pgw_column_kernel(const __grid_constant__ pgw_timestep_args a, const int lst, co
             const float g = fast_rcp(fmaf(-0.378f, e, fmaf(psn_f, m.y, m.x)));
             const double tv = fma(Td, (double)((0.61f * 0.622f) * e * g), Td);
             acc = fma(tv, ln_ratio<FAST>(pb, pref, lk), acc);
+        }
         }
         const double phi_pgw = fis + kRd * acc;
         const double err = (phi_pgw - phi_era) - gdzg;
