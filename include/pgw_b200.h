@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PGW_B200_ABI_VERSION 1
+#define PGW_B200_ABI_VERSION 2
 
 /* host-side return codes */
 #define PGW_OK               0
@@ -202,6 +202,10 @@ typedef struct pgw_timestep_args {
     const double *plev;         /* [nplev] in FILE order                       */
     /* HOST copies of ak, bk ([nlev+1]); used to size the shared-memory stash  */
     const double *ak_host, *bk_host;
+    /* HOST copies of akm, bkm ([nlev]); optional (may be NULL): with them, and with
+       ncol % 4 == 0 and 16-byte aligned 3-D fields, pgw_timestep() streams the 3-D
+       fields with TMA (cp.async.bulk.tensor) instead of per-thread copies          */
+    const double *akm_host, *bkm_host;
     /* ERA5 fields of one timestep, DEVICE float32 */
     const float *PS, *FIS, *FR_LAND, *FR_SEA_ICE, *T_SKIN;   /* [ncol]         */
     const float *T_SO;                                       /* [nsoil, ncol]  */
@@ -234,6 +238,9 @@ typedef struct pgw_timestep_args {
  * a negative PGW_E_* code */
 long long pgw_sizeof_timestep_args(void);   /* for FFI layout checks */
 long long pgw_timestep_smem_bytes(const pgw_timestep_args *a);
+/* 1 if pgw_timestep() takes the TMA flavour of the column kernel for these args, 0 if the
+ * per-thread cp.async flavour (odd ncol, unaligned fields, PGW_COLUMN_PATH=generic) */
+int pgw_timestep_uses_tma(const pgw_timestep_args *a);
 int pgw_timestep(const pgw_timestep_args *a, void *stream);
 
 /* device-side result of the convergence scan, written by finalize */

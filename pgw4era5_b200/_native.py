@@ -37,7 +37,7 @@ class TimestepArgs(C.Structure):
     _fields_ = (
         [("ncol", C.c_longlong), ("nlev", C.c_int), ("nplev", C.c_int), ("nsoil", C.c_int),
          ("plev_descending", C.c_int)]
-        + [(n, c_fp) for n in ("ak", "bk", "akm", "bkm", "plev", "ak_host", "bk_host")]
+        + [(n, c_fp) for n in ("ak", "bk", "akm", "bkm", "plev", "ak_host", "bk_host", "akm_host", "bkm_host")]
         + [(n, c_fp) for n in ("PS", "FIS", "FR_LAND", "FR_SEA_ICE", "T_SKIN", "T_SO", "T", "QV", "U", "V")]
         + [(n, TSlab) for n in ("ta", "hur", "ua", "va", "tas", "hurs", "ps_hist", "ts", "tos",
                                 "siconc", "zg_ref")]
@@ -85,6 +85,7 @@ def _load():
         "pgw_time_interp_f32": (i, [vp, vp, d, d, vp, ll, vp]),
         "pgw_time_mean_f32": (i, [vp, i, vp, ll, vp]),
         "pgw_timestep_smem_bytes": (ll, [C.POINTER(TimestepArgs)]),
+        "pgw_timestep_uses_tma": (i, [C.POINTER(TimestepArgs)]),
         "pgw_timestep": (i, [C.POINTER(TimestepArgs), vp]),
         "pgw_timestep_finalize": (i, [C.POINTER(TimestepArgs), vp, vp]),
         "pgw_zonal_mean_f32": (i, [vp, vp, ll, i, i, vp]),

@@ -23,7 +23,7 @@ int pgw_check_launch(const char *what) {
 }
 
 extern "C" {
-const char *pgw_version(void) { return "pgw_b200 0.1.0 (sm_100a, abi 1)"; }
+const char *pgw_version(void) { return "pgw_b200 0.2.0 (sm_100a, abi 2)"; }
 const char *pgw_last_error(void) { return g_last_error; }
 long long pgw_sizeof_timestep_args(void) { return (long long)sizeof(pgw_timestep_args); }
 }

@@ -247,6 +247,7 @@ class PGWEngine:
                                     self.bkm_d.data_ptr())
         a.plev = ds.plev_dev.data_ptr()
         a.ak_host, a.bk_host = self.ak.ctypes.data, self.bk.ctypes.data
+        a.akm_host, a.bkm_host = self.akm.ctypes.data, self.bkm.ctypes.data
         for name in ("PS", "FIS", "FR_LAND", "FR_SEA_ICE", "T_SKIN", "T", "QV", "U", "V"):
             setattr(a, name, f[name].data_ptr())
         a.T_SO = f["T_SO"].data_ptr() if nsoil else 0

@@ -195,3 +195,43 @@ def test_global_size_properties():
     assert r0["n_iter"] == 1
     for name in ("T", "U", "V", "PS"):
         assert torch.equal(r0[name].reshape(-1), era[name].reshape(-1)), name
+
+
+def _uses_tma(eng, era):
+    """Which flavour of the column kernel pgw_timestep() picked for the last submit."""
+    import ctypes as C
+    from pgw4era5_b200 import _native as N
+    p = eng.submit(_dev(era), ERA_DATE, ignore_top_pressure_error=True)
+    flag = N.lib.pgw_timestep_uses_tma(C.byref(p.args))
+    p.result()
+    return flag
+
+
+@pytest.mark.parametrize("ny,nx,seed", [(24, 40, 1), (16, 64, 11), (12, 44, 7)])
+def test_tma_and_generic_flavours_agree(ny, nx, seed, monkeypatch):
+    """ncol % 4 == 0 -> TMA flavour (incl. a partial last CTA); PGW_COLUMN_PATH=generic forces the
+    per-thread cp.async flavour.  Same arithmetic up to fma contraction (and one more parked
+    level), so the fields agree to rounding, and both must match the oracle."""
+    era, deltas = make_case(ny, nx, seed)
+    ref = run_oracle(era, deltas)
+    eng = _engine(era, deltas)
+    monkeypatch.delenv("PGW_COLUMN_PATH", raising=False)
+    assert _uses_tma(eng, era) == 1
+    res_t = eng.apply(_dev(era), ERA_DATE, ignore_top_pressure_error=True)
+    monkeypatch.setenv("PGW_COLUMN_PATH", "generic")
+    assert _uses_tma(eng, era) == 0
+    res_g = eng.apply(_dev(era), ERA_DATE, ignore_top_pressure_error=True)
+    _check(res_t, ref)
+    _check(res_g, ref)
+    assert res_t["n_iter"] == res_g["n_iter"]
+    for name in ("T", "U", "V", "T_SKIN", "T_SO", "FR_SEA_ICE"):
+        assert torch.equal(res_t[name].view(torch.int32), res_g[name].view(torch.int32)), name
+    assert float((res_t["PS"] - res_g["PS"]).abs().max()) <= 1e-5 * 1e5 * 2 ** -23 * 4     # few fp32 ulps of ps
+    assert float((res_t["QV"] - res_g["QV"]).abs().max()) <= 1e-9
+    np.testing.assert_allclose(res_t["phi_max_errors"], res_g["phi_max_errors"], rtol=1e-9)
+
+
+def test_odd_ncol_takes_generic_flavour():
+    era, deltas = make_case(7, 31, 3)
+    eng = _engine(era, deltas)
+    assert _uses_tma(eng, era) == 0
