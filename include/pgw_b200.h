@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PGW_B200_ABI_VERSION 2
+#define PGW_B200_ABI_VERSION 3
 
 /* host-side return codes */
 #define PGW_OK               0
@@ -211,7 +211,9 @@ typedef struct pgw_timestep_args {
     const float *T_SO;                                       /* [nsoil, ncol]  */
     const float *T, *QV, *U, *V;                             /* [nlev, ncol]   */
     /* climate deltas bracketing the ERA5 time */
-    pgw_tslab ta, hur, ua, va;          /* [nplev, ncol] each                  */
+    pgw_tslab d4;           /* ta, hur, ua, va deltas packed per node and column:
+                               float4 [nplev, ncol] = {ta, hur, ua, va}, 16-byte
+                               aligned (lo/hi point at float4 data)            */
     pgw_tslab tas, hurs, ps_hist, ts, tos, siconc;   /* [ncol]                 */
     pgw_tslab zg_ref;                   /* zg delta on the p_ref level, [ncol] */
     const float *ts_clim;               /* annual-mean ts delta [ncol]         */

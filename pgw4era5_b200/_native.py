@@ -39,8 +39,7 @@ class TimestepArgs(C.Structure):
          ("plev_descending", C.c_int)]
         + [(n, c_fp) for n in ("ak", "bk", "akm", "bkm", "plev", "ak_host", "bk_host", "akm_host", "bkm_host")]
         + [(n, c_fp) for n in ("PS", "FIS", "FR_LAND", "FR_SEA_ICE", "T_SKIN", "T_SO", "T", "QV", "U", "V")]
-        + [(n, TSlab) for n in ("ta", "hur", "ua", "va", "tas", "hurs", "ps_hist", "ts", "tos",
-                                "siconc", "zg_ref")]
+        + [(n, TSlab) for n in ("d4", "tas", "hurs", "ps_hist", "ts", "tos", "siconc", "zg_ref")]
         + [("ts_clim", c_fp), ("soil_decay", C.c_double * PGW_MAX_SOIL),
            ("p_ref", C.c_double), ("adj_factor", C.c_double),
            ("thresh_phi_ref_max_error", C.c_double), ("k_spec", C.c_int), ("ps_bound", C.c_double)]

@@ -1,0 +1,558 @@
+// The TMA flavour of the fused per-timestep column kernel of libpgw_b200 (sm_100a).
+//
+// Same algorithm and reference semantics as pgw_timestep.cu (see the header comment there):
+// one thread owns one ERA5 column, the column is swept bottom-up, the levels below p_ref are
+// parked in shared memory for the surface-pressure fixed point, the rest is streamed with the
+// adjusted surface pressure already known.  What differs is how the 3-D fields move:
+//
+//  * a fifth warp (one elected thread) streams level PAIRS of the CTA's 128 columns through a
+//    ring of shared-memory slots [T,QV,U,V][2 levels][128] with cp.async.bulk.tensor (TMA,
+//    box 2 x 128 of a [nlev, ncol] tensor map per field);
+//  * the four column warps wait on full[slot], read their column from the slot, compute, write
+//    the results back IN PLACE, fence them for the async proxy and arrive on done[slot];
+//  * the producer then stores the slot with TMA (bulk group), and, once the previous slot's
+//    store has left shared memory, refills that slot with the pair kTmaSlots ahead.  Pairs
+//    further ahead are pulled into L2 with cp.async.bulk.prefetch.tensor.
+//
+// Per-thread global accesses are left only for the 2-D fields, the delta nodes and QV of the
+// parked levels.  The column threads execute one streaming loop for all 69 level pairs (the
+// fixed point runs inside it, between the last parked pair and the first streamed one), and ONE
+// delta walker serves all four variables: the packed float4 deltas (ta, hur, ua, va) share their
+// pressure nodes, and the surface node that replace_delta_sfc (functions.py:343-366) inserts into
+// the ta/hur columns only matters below the node under ps_hist, where it is applied as an override.
+// Both keep the hot code small: the previous version was instruction-cache bound.
+//
+// Needs ncol % 4 == 0 (16-byte global strides), 16-byte aligned fields and nlev <= kTmaMaxLev;
+// anything else takes the cp.async flavour.
+#include "pgw_column.cuh"
+
+#include <stdlib.h>
+#include <string.h>
+
+namespace pgw {
+
+constexpr int kTmaSlots = 4;         // ring of level pairs, 4 KB each
+constexpr int kTmaL2Ahead = 6;       // level pairs prefetched into L2 beyond the ones in the ring
+constexpr int kTmaMaxLev = 160;      // capacity of the parameter-space table of the upper levels
+
+// tiled tensor maps [nlev, ncol] (box 2 x 128) of the four 3-D inputs and outputs, and (akm, bkm)
+// as float2 for the levels above the stash, read through the constant bank
+struct TmaParams {
+    CUtensorMap in[4];      // T, QV, U, V
+    CUtensorMap out[4];     // T_out, QV_out, U_out, V_out
+    float2 m[kTmaMaxLev];
+};
+
+struct F4 { float x, y, z, w; };
+__device__ __forceinline__ F4 ldg4(const float4 *p) { const float4 v = __ldg(p); return F4{v.x, v.y, v.z, v.w}; }
+
+template <bool FAST>
+__global__ void __launch_bounds__(kColumnThreads + 32, 3)
+pgw_column_tma_kernel(const __grid_constant__ pgw_timestep_args a, const __grid_constant__ TmaParams tp,
+                      const int lst, const int np) {
+    constexpr int NT = kColumnThreads;
+    constexpr int SM = kTmaSlots - 1;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int L = a.nlev, K = a.nplev;
+    // ---- shared memory: pair ring | stash | (ak,bk)[np+1] | (akm,bkm)[np] | plev tables | barriers
+    float *const ring = reinterpret_cast<float *>(smem);                          // [kTmaSlots][4][2][NT]
+    float2 *const st_Te = reinterpret_cast<float2 *>(ring + kTmaSlots * 8 * NT);    // [np][NT] (T_pgw fp32, e_pgw)
+    double2 *const hl0 = reinterpret_cast<double2 *>(st_Te + (size_t)np * NT);
+    float2 *const m0p = reinterpret_cast<float2 *>(hl0 + (np + 1));
+    float *const s_plev = reinterpret_cast<float *>(m0p + np);                     // [K] ascending
+    float *const s_inv_plev = s_plev + K;                                          // [K]
+    float *const s_inv_w = s_inv_plev + K;                                         // [K] 1/log2(p[j+1]/p[j])
+    uint64_t *const bar_full = reinterpret_cast<uint64_t *>(s_plev + 3 * K + ((3 * K) & 1));
+    uint64_t *const bar_done = bar_full + kTmaSlots;
+    const double2 *const s_hl = hl0 - lst;      // indexed by the half level, l >= lst
+    const float2 *const s_m = m0p - lst;        // indexed by the full level, l >= lst
+
+    const int tid = threadIdx.x;
+    for (int i = tid; i <= np; i += NT + 32) hl0[i] = make_double2(a.ak[lst + i], a.bk[lst + i]);
+    for (int i = tid; i < np; i += NT + 32) m0p[i] = make_float2((float)a.akm[lst + i], (float)a.bkm[lst + i]);
+    for (int i = tid; i < K; i += NT + 32) {
+        const int f0 = a.plev_descending ? (K - 1 - i) : i;
+        const float p0 = (float)a.plev[f0];
+        s_plev[i] = p0;
+        s_inv_plev[i] = 1.0f / p0;
+        if (i + 1 < K) {
+            const float p1 = (float)a.plev[a.plev_descending ? (K - 2 - i) : (i + 1)];
+            s_inv_w[i] = 1.0f / log2f(p1 / p0);
+        } else s_inv_w[i] = 0.0f;
+    }
+    if (tid == 0) {
+        for (int i = 0; i < kTmaSlots; ++i) { mbar_init(bar_full + i, 1); mbar_init(bar_done + i, NT); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const uint32_t n = (uint32_t)a.ncol;
+    const int npairs = (L + 1) >> 1, np1 = np >> 1;     // level pairs in total / parked (np is even)
+
+    // ------------------------------------------------------------------ producer warp
+    if (tid >= NT) {
+        if (tid != NT) return;
+        const int c0 = (int)(blockIdx.x * NT);
+        // pair j = levels L-1-2j (row 1) and L-2-2j (row 0).  TMA coordinates must not be negative,
+        // so the last pair of an odd column is levels (1, 0): level 1 is simply done twice.
+        auto pair_row = [&](int j) { const int r = L - 2 - 2 * j; return r < 0 ? 0 : r; };
+        auto load_pair_slot = [&](int j) {
+            const int s = j & SM;
+            float *dst = ring + s * 8 * NT;
+            mbar_arrive_expect_tx(bar_full + s, 4u * 2u * NT * sizeof(float));
+#pragma unroll
+            for (int v = 0; v < 4; ++v) tma_load_2d(dst + v * 2 * NT, &tp.in[v], c0, pair_row(j), bar_full + s);
+        };
+        auto l2_pair = [&](int j) {
+            if (j < npairs) {
+#pragma unroll
+                for (int v = 0; v < 4; ++v) tma_prefetch_2d(&tp.in[v], c0, pair_row(j));
+            }
+        };
+        for (int j = 0; j < kTmaSlots && j < npairs; ++j) load_pair_slot(j);
+        for (int j = kTmaSlots; j < kTmaSlots + kTmaL2Ahead; ++j) l2_pair(j);
+#pragma unroll 1
+        for (int j = 0; j < npairs; ++j) {
+            const int s = j & SM;
+            const float *src = ring + s * 8 * NT;
+            mbar_wait_backoff(bar_done + s, (j / kTmaSlots) & 1);
+            const int row = pair_row(j);
+            tma_store_2d(&tp.out[0], c0, row, src);
+            if (j >= np1) tma_store_2d(&tp.out[1], c0, row, src + 2 * NT);   // QV of the parked levels: phase 3
+            tma_store_2d(&tp.out[2], c0, row, src + 4 * NT);
+            tma_store_2d(&tp.out[3], c0, row, src + 6 * NT);
+            tma_commit();
+            tma_wait_read<1>();                     // the stores of pair j-1 have left shared memory
+            if (j >= 1 && j - 1 + kTmaSlots < npairs) load_pair_slot(j - 1 + kTmaSlots);
+            l2_pair(j + kTmaSlots + kTmaL2Ahead);
+        }
+        tma_wait_all();
+        return;
+    }
+
+    // ------------------------------------------------------------------ column threads
+    const uint32_t c_raw = blockIdx.x * NT + tid;
+    // Threads past the last column read column n-1 for the 2-D fields; their slot columns are
+    // zero-filled by TMA and clipped on store, and their per-thread stores are masked.
+    const uint32_t c = (c_raw >= n) ? n - 1 : c_raw;
+    const bool valid = c_raw < n;
+    unsigned errbits = 0;
+
+    // ---------------- surface, skin and soil (step_03:103-146) ----------------
+    const float ps_f = __ldg(a.PS + c);
+    const Pair2 r_sic = load_pair(a.siconc, c), r_ts = load_pair(a.ts, c), r_tos = load_pair(a.tos, c);
+    const Pair2 r_psh = load_pair(a.ps_hist, c), r_tas = load_pair(a.tas, c), r_hurs = load_pair(a.hurs, c);
+    const Pair2 r_zg = load_pair(a.zg_ref, c);
+    const float r_ice = __ldg(a.FR_SEA_ICE + c), r_land = __ldg(a.FR_LAND + c), r_skin = __ldg(a.T_SKIN + c);
+    const float r_clim = __ldg(a.ts_clim + c), r_fis = __ldg(a.FIS + c);
+    const double PSd = (double)ps_f;
+
+    // ---------------- the delta walker (functions.py:343-431, 511-580) ----------------
+    // Downward merge walk over the pressure-ascending nodes: state = lo node (index, pressure,
+    // values of the four variables) and the differences to the hi node; inv_w == 0 encodes
+    // "no interpolation" (at/after the last node, or above node 0): the lo values are returned.
+    // Nodes lo-1 and lo-2 are prefetched as raw (before, after) time slabs and blended when used;
+    // nodes further down are pulled into L2.
+    const float w_t = slab_weight(a.d4);
+    const float4 *const d4lo = reinterpret_cast<const float4 *>(a.d4.lo);
+    const float4 *const d4hi = reinterpret_cast<const float4 *>(a.d4.hi);
+    const int desc = a.plev_descending;
+    auto node_off = [&](int j) { return (uint32_t)(desc ? (K - 1 - j) : j) * n + c; };
+    auto blend4 = [&](const F4 &x0, const F4 &x1) {
+        return F4{blend_f32(w_t, x0.x, x1.x), blend_f32(w_t, x0.y, x1.y), blend_f32(w_t, x0.z, x1.z),
+                  blend_f32(w_t, x0.w, x1.w)};
+    };
+    auto l2_node = [&](int j) {
+        const uint32_t off = node_off(j);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(d4lo + off));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(d4hi + off));
+    };
+
+    const float2 m_bot = s_m[L - 1];
+    const float p_bot = fmaf(ps_f, m_bot.y, m_bot.x);           // the first level of the sweep
+    int w_lo = -1;                                              // max{k: plev[k] <= p_bot}
+    for (int k = K - 1; k >= 0; --k)
+        if (s_plev[k] <= p_bot) { w_lo = k; break; }
+    // replace_delta_sfc: node s of the ta/hur columns carries (ps_hist, surface delta) and all
+    // nodes after it hold the surface delta.  s = max{k: plev[k] < ps_hist}.
+    const float psh = (float)blend_f64(a.ps_hist, r_psh);
+    int s_node = K - 1;
+    if (!(psh > s_plev[K - 1])) {
+        s_node = -1;
+        for (int k = K - 1; k >= 0; --k)
+            if (s_plev[k] < psh) { s_node = k; break; }
+    }
+    if (s_node < 0) { errbits |= PGW_ERR_PS_HIST_RANGE; s_node = 0; }
+    const float min_src_p0 = (s_node == 0) ? psh : s_plev[0];
+
+    // raw nodes: hi = w_lo+1, lo = w_lo, then the two prefetched ones, and node s-1 for the override
+    const int j_lo = w_lo < 0 ? 0 : w_lo, j_hi = (w_lo >= 0 && w_lo + 1 < K) ? w_lo + 1 : j_lo;
+    const F4 rl0 = ldg4(d4lo + node_off(j_lo)), rl1 = ldg4(d4hi + node_off(j_lo));
+    const F4 rh0 = ldg4(d4lo + node_off(j_hi)), rh1 = ldg4(d4hi + node_off(j_hi));
+    const int j_s1 = s_node >= 1 ? s_node - 1 : 0;
+    const F4 rs0 = ldg4(d4lo + node_off(j_s1)), rs1 = ldg4(d4hi + node_off(j_s1));
+    F4 n0{0.f, 0.f, 0.f, 0.f}, n1 = n0, m0 = n0, m1 = n0;       // raw slabs of nodes lo-1, lo-2
+    if (w_lo >= 1) { n0 = ldg4(d4lo + node_off(w_lo - 1)); n1 = ldg4(d4hi + node_off(w_lo - 1)); }
+    if (w_lo >= 2) { m0 = ldg4(d4lo + node_off(w_lo - 2)); m1 = ldg4(d4hi + node_off(w_lo - 2)); }
+#pragma unroll
+    for (int d = 3; d <= kL2Ahead; ++d)
+        if (w_lo - d >= 0) l2_node(w_lo - d);
+
+    {
+        // FR_SEA_ICE is float32 in the file and updated in place there
+        float sic = (float)((double)r_ice + blend_f64(a.siconc, r_sic) / 100.0);
+        sic = sic < 0.0f ? 0.0f : (sic > 1.0f ? 1.0f : sic);           // np.clip keeps NaN
+        const double dts = blend_f64(a.ts, r_ts);
+        const double dtos = blend_f64(a.tos, r_tos);
+        double comb = dts;                                            // integrate_tos
+        if (!isnan(sic) && !isnan(dtos)) {
+            float fr = sic + r_land;
+            fr = fr < 0.0f ? 0.0f : (fr > 1.0f ? 1.0f : fr);
+            comb = (double)fr * dts + (double)(1.0f - fr) * dtos;
+        }
+        const double clim = (double)r_clim;
+        if (valid) {
+            a.FR_SEA_ICE_out[c] = sic;
+            a.T_SKIN_out[c] = (float)((double)r_skin + comb);
+        }
+        for (int s = 0; s < a.nsoil; ++s) {
+            const double dso = clim + a.soil_decay[s] * (comb - clim);
+            const float so = (float)((double)__ldg(a.T_SO + (uint32_t)s * n + c) + dso);
+            if (valid) a.T_SO_out[(uint32_t)s * n + c] = so;
+        }
+    }
+
+    // walker state
+    float w_p_lo, w_inv_p_lo, w_inv_w;
+    F4 x_lo = blend4(rl0, rl1), x_d{0.f, 0.f, 0.f, 0.f};
+    if (w_lo >= 0) {
+        w_p_lo = s_plev[w_lo]; w_inv_p_lo = s_inv_plev[w_lo]; w_inv_w = s_inv_w[w_lo];   // inv_w[K-1] == 0
+        if (w_lo + 1 < K) {
+            const F4 x_hi = blend4(rh0, rh1);
+            x_d = F4{x_hi.x - x_lo.x, x_hi.y - x_lo.y, x_hi.z - x_lo.z, x_hi.w - x_lo.w};
+        }
+    } else {
+        w_p_lo = 0.0f; w_inv_p_lo = 1.0f; w_inv_w = 0.0f;       // whole column above node 0
+    }
+    // Override for ta, hur while p > plev[s-1]: the surface delta for p >= ps_hist, else the segment
+    // between node s-1 and the (ps_hist, surface delta) node.  s == 0: the surface delta everywhere.
+    const float sfc_ta = (float)blend_f64(a.tas, r_tas), sfc_hur = (float)blend_f64(a.hurs, r_hurs);
+    bool bot_on = true;
+    float b_p1, b_inv_p1, b_inv_w, b_psh, b_ta1, b_hur1, b_dta, b_dhur;
+    {
+        const F4 xs = blend4(rs0, rs1);
+        const bool has = s_node >= 1;
+        b_p1 = has ? s_plev[j_s1] : 0.0f;
+        b_inv_p1 = has ? s_inv_plev[j_s1] : 1.0f;
+        b_psh = has ? psh : 0.0f;
+        b_inv_w = has ? fast_rcp(fast_lg2(psh * b_inv_p1)) : 0.0f;
+        b_ta1 = has ? xs.x : sfc_ta; b_hur1 = has ? xs.y : sfc_hur;
+        b_dta = sfc_ta - b_ta1; b_dhur = sfc_hur - b_hur1;
+    }
+
+    struct Dlt { float ta, hur, ua, va; };
+    auto walk = [&](float p) {
+        while (w_p_lo > p) {
+            const F4 hi = x_lo;
+            --w_lo;
+            if (w_lo >= 0) {
+                w_p_lo = s_plev[w_lo]; w_inv_p_lo = s_inv_plev[w_lo]; w_inv_w = s_inv_w[w_lo];
+                x_lo = blend4(n0, n1);
+                x_d = F4{hi.x - x_lo.x, hi.y - x_lo.y, hi.z - x_lo.z, hi.w - x_lo.w};
+                n0 = m0; n1 = m1;
+                // the new loads are ordered behind the reads of the registers they replace
+                const int zero = reg_fence(n1.x, n1.y, n1.z, n1.w);
+                if (w_lo >= 2) { const uint32_t off = node_off(w_lo - 2 + zero); m0 = ldg4(d4lo + off); m1 = ldg4(d4hi + off); }
+                if (w_lo >= kL2Ahead) l2_node(w_lo - kL2Ahead);
+            } else {
+                // above node 0: constant extrapolation with node 0's values; p_lo = 0 ends the walk
+                x_d = F4{0.f, 0.f, 0.f, 0.f}; w_inv_w = 0.0f; w_p_lo = 0.0f; w_inv_p_lo = 1.0f;
+            }
+        }
+        const float t = fast_lg2(p * w_inv_p_lo) * w_inv_w;
+        // t == 0: exact node hit or constant extrapolation -> the node value itself (NaN-safe)
+        const bool ex = (t == 0.0f);
+        Dlt d;
+        d.ta = ex ? x_lo.x : fmaf(t, x_d.x, x_lo.x);
+        d.hur = ex ? x_lo.y : fmaf(t, x_d.y, x_lo.y);
+        d.ua = ex ? x_lo.z : fmaf(t, x_d.z, x_lo.z);
+        d.va = ex ? x_lo.w : fmaf(t, x_d.w, x_lo.w);
+        return d;
+    };
+    auto sfc_override = [&](float p, Dlt &d) {
+        if (bot_on) {
+            if (p > b_p1) {
+                const float tb = fast_lg2(p * b_inv_p1) * b_inv_w;
+                const bool below = p >= b_psh;
+                d.ta = below ? sfc_ta : fmaf(tb, b_dta, b_ta1);
+                d.hur = below ? sfc_hur : fmaf(tb, b_dhur, b_hur1);
+            } else bot_on = false;
+        }
+    };
+
+    LnConst lk{2.0 / 3.0, 2.0 / 5.0, 2.0 / 7.0};
+    asm volatile("" : "+d"(lk.c3), "+d"(lk.c5), "+d"(lk.c7));     // keep the constants in registers
+
+    const double pref = a.p_ref;
+    const double2 hl_sfc = s_hl[L];
+    double pb_era = fma(PSd, hl_sfc.y, hl_sfc.x);
+    double acc_era = 0.0;
+    bool era_open = pb_era >= pref;                 // still below p_ref
+    if (!era_open) errbits |= PGW_ERR_PREF_BELOW_SFC;
+    float psn_f = ps_f;                             // ps used for QV; replaced after the iteration
+
+    // T_pgw is parked as fp32.  Its rounding residual r_l (|r_l| <= 1.5e-5 K) enters the
+    // geopotential as Rd * sum_l r_l dlnp_l; that sum is taken once with the ERA pressures
+    // (its change over the iteration is < 1e-8 m2/s2) and added to every iteration's sum.
+    double acc_res = 0.0, acc_pgw0 = 0.0, t_low_d = 0.0;
+    // ERA geopotential of one layer (functions.py:128-189), sequential in the column.  The first
+    // iteration of the fixed point (dps = 0) integrates the PGW state over the same pressures, so
+    // its sum is taken here as well and the iteration proper starts at k = 1.
+    auto era_layer = [&](int l, float p, float t, float q, float dta, float t_pgw, float e_pgw) {
+        if (era_open) {
+            const double2 hl = s_hl[l];
+            double pt = fma(PSd, hl.y, hl.x);
+            if (pt < pref) { pt = pref; era_open = false; }     // layer that contains p_ref (:174-179)
+            const double td = (double)t, tpd = (double)t_pgw;
+            const double tv = fma(td, 0.61 * (double)q, td);
+            const float g = fast_rcp(fmaf(-0.378f, e_pgw, p));
+            const double tvp = fma(tpd, (double)((0.61f * 0.622f) * e_pgw * g), tpd);
+            const double dl = ln_ratio<FAST>(pb_era, pt, lk);
+            acc_era = fma(tv, dl, acc_era);
+            acc_pgw0 = fma(tvp, dl, acc_pgw0);
+            acc_res = fma((td + (double)dta) - tpd, dl, acc_res);
+            pb_era = pt;
+        }
+    };
+
+    // ---------------- phase 2: surface-pressure fixed point (step_03:182-319) ----------------
+    // and phase 3a: PS and QV of the parked levels.  Runs once, between the parked and the
+    // streamed pairs; the TMA loads of the next pairs are in flight meanwhile.
+    auto fixed_point = [&]() {
+        const double fis = (double)r_fis;
+        const double phi_era = fis + kRd * acc_era;
+        const double gdzg = blend_f64(a.zg_ref, r_zg) * kG;              // step_03:292-295
+        const float2 *const bTe = st_Te + (size_t)(L - 1 - lst) * NT + tid;  // lowest level of the stash
+        const double t_low = t_low_d;                                 // ta_pgw on the lowest level
+        double dps = 0.0, adj = 0.0, psn = PSd;
+        int ltop = lst + 1;                 // first layer (from the top) lying entirely below p_ref
+        float *traj = a.dps_traj + c;
+        for (int k = 0; k < a.k_spec; ++k, traj += n) {
+            dps += adj;
+            psn = PSd + dps;
+            psn_f = (float)psn;
+            if (valid) *traj = (float)dps;
+            if (psn > a.ps_bound) errbits |= PGW_ERR_PS_BOUND;
+            double pb = fma(psn, hl_sfc.y, hl_sfc.x);
+            if (pb < pref) errbits |= PGW_ERR_PREF_BELOW_SFC;
+            double acc = acc_res;
+            if (k == 0) {
+                acc += acc_pgw0;            // psn == PS: summed in phase 1 together with the ERA state
+            } else {
+                // layers ltop..L-1 are entirely below p_ref for this ps; it moves by at most a level or two
+                while (ltop > lst) { const double2 h = s_hl[ltop - 1]; if (fma(psn, h.y, h.x) >= pref) --ltop; else break; }
+                while (ltop < L) { const double2 h = s_hl[ltop]; if (fma(psn, h.y, h.x) < pref) ++ltop; else break; }
+                const float2 *pTe = bTe;
+                int l = L - 1;
+#pragma unroll 4
+                for (; l >= ltop; --l, pTe -= NT) {
+                    const double2 hl = s_hl[l];
+                    const float2 m = s_m[l];
+                    const float2 te = *pTe;
+                    const float e = te.y;
+                    const double Td = (double)te.x;
+                    const double pt = fma(psn, hl.y, hl.x);
+                    // Tv = T (1 + 0.61 hus), hus = 0.622 e / (p - 0.378 e)   (functions.py:66-72, :144)
+                    const float g = fast_rcp(fmaf(-0.378f, e, fmaf(psn_f, m.y, m.x)));
+                    const double tv = fma(Td, (double)((0.61f * 0.622f) * e * g), Td);
+                    acc = fma(tv, ln_ratio<FAST>(pb, pt, lk), acc);
+                    pb = pt;
+                }
+                if (l >= lst && pb >= pref) {                              // layer that contains p_ref (:174-179)
+                    const float2 m = s_m[l];
+                    const float2 te = *pTe;
+                    const float e = te.y;
+                    const double Td = (double)te.x;
+                    const float g = fast_rcp(fmaf(-0.378f, e, fmaf(psn_f, m.y, m.x)));
+                    const double tv = fma(Td, (double)((0.61f * 0.622f) * e * g), Td);
+                    acc = fma(tv, ln_ratio<FAST>(pb, pref, lk), acc);
+                }
+            }
+            const double phi_pgw = fis + kRd * acc;
+            const double err = (phi_pgw - phi_era) - gdzg;
+            adj = -a.adj_factor * psn / (kRd * t_low) * err;
+            double ae = (isnan(err) || !valid) ? 0.0 : fabs(err);      // max skips NaN (step_03:308)
+            ae = warp_max(ae);
+            if ((tid & 31) == 0 && ae > 0.0)
+                atomicMax(reinterpret_cast<unsigned long long *>(a.maxerr + k),
+                          (unsigned long long)__double_as_longlong(ae));
+        }
+        if (valid) {
+            a.PS_out[c] = psn_f;
+            a.dps_out[c] = (float)dps;
+        }
+        const float2 *pTe = bTe;
+        uint32_t o2 = (uint32_t)(L - 1) * n + c;
+        float *const oQ = a.QV_out;
+        for (int l = L - 1; l >= lst; --l, pTe -= NT, o2 -= n) {
+            const float qv = qv_from_e(pTe->y, psn_f, s_m[l]);
+            if (valid) st_stream(oQ + o2, qv);
+        }
+    };
+
+    // ---------------- the sweep: parked pairs, fixed point, streamed pairs ----------------
+    float2 *pTe = st_Te + (size_t)(L - 1 - lst) * NT + tid;
+#pragma unroll 1
+    for (int j = 0; j <= npairs; ++j) {
+        const bool parked = j < np1;
+        if (j == np1) fixed_point();                  // np1 <= npairs: exactly once
+        if (j == npairs) break;
+        const int l = max(L - 1 - 2 * j, 1);          // last pair of an odd column: levels (1, 0) again
+        float2 mm0, mm1;
+        if (parked) { mm0 = s_m[l]; mm1 = s_m[l - 1]; } else { mm0 = tp.m[l]; mm1 = tp.m[l - 1]; }
+        float *const sl = ring + (j & SM) * 8 * NT + tid;
+        mbar_wait(bar_full + (j & SM), (j / kTmaSlots) & 1);
+        const float t0 = sl[NT], q0 = sl[3 * NT], u0 = sl[5 * NT], v0 = sl[7 * NT];    // row 1: level l
+        const float t1 = sl[0], q1 = sl[2 * NT], u1 = sl[4 * NT], v1 = sl[6 * NT];     // row 0: level l-1
+        const float p0 = fmaf(ps_f, mm0.y, mm0.x), p1 = fmaf(ps_f, mm1.y, mm1.x);
+        Dlt d0 = walk(p0);
+        Dlt d1 = walk(p1);
+        if (__any_sync(0xffffffffu, bot_on)) { sfc_override(p0, d0); sfc_override(p1, d1); }
+        const bool cold = __all_sync(0xffffffffu, is_cold(t0, d0.ta) && is_cold(t1, d1.ta));
+        const float e0 = thermo_e_pgw(cold, p0, t0, q0, d0.ta, d0.hur);
+        const float e1 = thermo_e_pgw(cold, p1, t1, q1, d1.ta, d1.hur);
+        const float tp0 = t0 + d0.ta, tp1 = t1 + d1.ta;   // == (float)((double)t + (double)dta)
+        sl[NT] = tp0; sl[5 * NT] = u0 + d0.ua; sl[7 * NT] = v0 + d0.va;
+        sl[0] = tp1; sl[4 * NT] = u1 + d1.ua; sl[6 * NT] = v1 + d1.va;
+        if (parked) {
+            fence_proxy_async();
+            mbar_arrive(bar_done + (j & SM));
+            pTe[0] = make_float2(tp0, e0);
+            pTe[-NT] = make_float2(tp1, e1);
+            pTe -= 2 * NT;
+            if (j == 0) t_low_d = (double)t0 + (double)d0.ta;
+            era_layer(l, p0, t0, q0, d0.ta, tp0, e0);
+            era_layer(l - 1, p1, t1, q1, d1.ta, tp1, e1);
+        } else {
+            sl[3 * NT] = qv_from_e(e0, psn_f, mm0);       // functions.py:66-72 with the adjusted ps
+            sl[2 * NT] = qv_from_e(e1, psn_f, mm1);
+            fence_proxy_async();
+            mbar_arrive(bar_done + (j & SM));
+        }
+    }
+
+    // ---------------- bookkeeping for the host-side checks ----------------
+    const float2 m_top = tp.m[0];
+    float p_top = fmaf(ps_f, m_top.y, m_top.x);                          // functions.py:417
+    p_top = warp_min(p_top);
+    const float min_src_p = warp_min(min_src_p0);
+    if ((tid & 31) == 0) {
+        atomicMin(reinterpret_cast<unsigned *>(a.stats), __float_as_uint(fmaxf(p_top, 0.0f)));
+        atomicMin(reinterpret_cast<unsigned *>(a.stats) + 1, __float_as_uint(fmaxf(min_src_p, 0.0f)));
+    }
+    if (errbits && valid) atomicOr(a.err, errbits);
+}
+
+}  // namespace pgw
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+namespace {
+
+using pgw::kColumnThreads;
+
+size_t column_smem_tma(int nplev, int np) {
+    const int nt = kColumnThreads;
+    size_t b = sizeof(float) * (size_t)pgw::kTmaSlots * 8 * nt +            // pair ring
+               (size_t)np * nt * (2 * sizeof(float)) +                      // stash
+               sizeof(double) * 2 * (size_t)(np + 1) + sizeof(float) * 2 * (size_t)np;
+    b += sizeof(float) * (size_t)(3 * nplev + ((3 * nplev) & 1));
+    b += sizeof(uint64_t) * 2 * pgw::kTmaSlots;
+    return b;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+// libcuda is not linked: the encoder is looked up through the runtime
+EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        cudaGetLastError();
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int make_map(CUtensorMap *m, const float *base, long long ncol, int nlev) {
+    const cuuint64_t dims[2] = {(cuuint64_t)ncol, (cuuint64_t)nlev};
+    const cuuint64_t strides[1] = {(cuuint64_t)ncol * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)kColumnThreads, 2u};
+    const cuuint32_t estr[2] = {1u, 1u};
+    CUresult r = encode_tiled()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box,
+                                estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        pgw_set_error("cuTensorMapEncodeTiled failed (%d)", (int)r);
+        return PGW_E_LAUNCH;
+    }
+    return PGW_OK;
+}
+
+}  // namespace
+
+bool pgw_tma_eligible(const pgw_timestep_args *a, int lst_generic, int *lst_tma, size_t *smem) {
+    const int np = a->nlev - lst_generic;
+    const int lst_even = lst_generic - (np & 1);        // whole level pairs are parked
+    if (!(a->akm_host && a->bkm_host) || lst_even < 0 || a->nlev > pgw::kTmaMaxLev || a->ncol % 4 != 0 ||
+        a->ncol < kColumnThreads || a->ncol >= (1ll << 31))
+        return false;
+    const void *f[8] = {a->T, a->QV, a->U, a->V, a->T_out, a->QV_out, a->U_out, a->V_out};
+    for (const void *p : f) if (!aligned16(p)) return false;
+    if (!encode_tiled()) return false;
+    *lst_tma = lst_even;
+    *smem = column_smem_tma(a->nplev, a->nlev - lst_even);
+    return true;
+}
+
+int pgw_launch_column_tma(const pgw_timestep_args *a, const pgw_column_plan &plan, cudaStream_t st) {
+    int rc;
+    pgw::TmaParams tp;
+    const float *in[4] = {a->T, a->QV, a->U, a->V};
+    float *out[4] = {a->T_out, a->QV_out, a->U_out, a->V_out};
+    for (int v = 0; v < 4; ++v) {
+        if ((rc = make_map(&tp.in[v], in[v], a->ncol, a->nlev)) != PGW_OK) return rc;
+        if ((rc = make_map(&tp.out[v], out[v], a->ncol, a->nlev)) != PGW_OK) return rc;
+    }
+    for (int l = 0; l < pgw::kTmaMaxLev; ++l)
+        tp.m[l] = l < a->nlev ? make_float2((float)a->akm_host[l], (float)a->bkm_host[l]) : make_float2(0.f, 0.f);
+    auto kern = plan.fast ? pgw::pgw_column_tma_kernel<true> : pgw::pgw_column_tma_kernel<false>;
+    static thread_local size_t configured[2] = {0, 0};
+    size_t &conf = configured[plan.fast ? 1 : 0];
+    if (plan.smem > conf) {
+        int dev = 0, max_optin = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        if (plan.smem > (size_t)max_optin) {
+            pgw_set_error("column stash needs %zu B of shared memory (%d levels below p_ref), device allows %d",
+                          plan.smem, plan.np, max_optin);
+            return PGW_E_SMEM;
+        }
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem) != cudaSuccess)
+            return pgw_check_launch("cudaFuncSetAttribute");
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        conf = plan.smem;
+    }
+    const unsigned grid = (unsigned)((a->ncol + kColumnThreads - 1) / kColumnThreads);
+    kern<<<grid, kColumnThreads + 32, plan.smem, st>>>(*a, tp, plan.lst, plan.np);
+    return pgw_check_launch("pgw_column_tma_kernel");
+}

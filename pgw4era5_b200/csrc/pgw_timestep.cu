@@ -17,134 +17,13 @@
 //   step_03_apply_to_era.py:158-173  delta application
 //   step_03_apply_to_era.py:182-319  surface-pressure fixed point
 //   functions.py:118-125, 128-189    hus from RH, geopotential integration
-#include "pgw_common.cuh"
+#include "pgw_column.cuh"
 
-#include <cuda.h>
 #include <cuda_pipeline.h>
-
 #include <stdlib.h>
 #include <string.h>
 
-#include <type_traits>
-
 namespace pgw {
-
-// ---------------------------------------------------------------------------
-// TMA / mbarrier primitives (sm_100a) used by the TMA flavour of the column kernel.
-// ---------------------------------------------------------------------------
-constexpr int kTmaSlots = 4;         // ring of level PAIRS, each [4 arrays][2 levels][128 columns] fp32
-constexpr int kTmaL2Ahead = 6;      // level pairs prefetched into L2 beyond the ones in the ring
-constexpr int kTmaMaxLev = 160;      // capacity of the parameter-space table of the upper levels
-
-// Kernel parameters of the TMA flavour: tiled tensor maps [nlev, ncol] (box 2 x 128) of the four
-// 3-D inputs and outputs, and (akm, bkm) as float2 for the levels above the stash, which are read
-// through the constant bank instead of shared memory.
-struct TmaParams {
-    CUtensorMap in[4];      // T, QV, U, V
-    CUtensorMap out[4];     // T_out, QV_out, U_out, V_out
-    float2 m[kTmaMaxLev];
-};
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "PGW_WAIT:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra PGW_DONE;\n\t"
-        "bra PGW_WAIT;\n\t"
-        "PGW_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-// generic-proxy writes to shared memory -> visible to the async proxy (TMA store)
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, int c0, int c1, const void *src) {
-    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
-                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(src)) : "memory");
-}
-// pull a box into L2 only (no shared-memory slot needed): hides the DRAM part of the latency
-__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap *map, int c0, int c1) {
-    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];"
-                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void tma_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-
-// Raw (before, after) pair of a 2-D delta; all pairs of a column are loaded up front so
-// that their DRAM latencies overlap, then blended.
-struct Pair2 { float lo, hi; };
-__device__ __forceinline__ Pair2 load_pair(const pgw_tslab &s, uint32_t off) {
-    Pair2 r;
-    r.lo = __ldg(s.lo + off);
-    r.hi = __ldg(s.hi + off);      // == lo slab for an exact hit (x_new == 0)
-    return r;
-}
-// scipy interp1d._call_linear with x = [0, x_hi]: slope * x_new + y_lo (float64)
-__device__ __forceinline__ double blend_f64(const pgw_tslab &s, const Pair2 &v) {
-    const double lo = (double)v.lo;
-    if (s.x_new == 0.0) return lo;
-    return ((double)v.hi - lo) / s.x_hi * s.x_new + lo;
-}
-
-__device__ __forceinline__ float fast_rcp(float x) {
-    float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-__device__ __forceinline__ float fast_lg2(float x) {
-    float r;
-    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-__device__ __forceinline__ float fast_ex2(float x) {
-    float r;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-// MUFU.RCP64H: >= 20 good bits of 1/x in one instruction
-__device__ __forceinline__ double rcp64_approx(double x) {
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    return r;
-}
-
-// ln(pb/pt), pb >= pt > 0, in float64 without a float64 log or divide:
-// 2 atanh(s), s = (pb-pt)/(pb+pt) = 2 s (1 + s^2/3 + s^4/5 + s^6/7 + ...).
-// Truncated after s^6/7 the relative error is s^8/9 < 2e-11 for s < 0.06, far below
-// the 1e-9 the ps iteration needs; all adjacent ERA5 half levels below ~100 hPa
-// have s < 0.05.  FAST = the host has verified s < 0.06 for every layer the
-// iteration can touch, so the exact-log branch is compiled out.
-struct LnConst { double c3, c5, c7; };
-
-template <bool FAST>
-__device__ __forceinline__ double ln_ratio(double pb, double pt, const LnConst &k) {
-    const double d = pb - pt;
-    const double sm = pb + pt;
-    double r = rcp64_approx(sm);
-    r = fma(r, fma(-sm, r, 1.0), r);            // one Newton step: ~1e-12 relative
-    const double s = d * r;
-    if (!FAST) { if (s > 0.06) return log(pb / pt); }
-    const double s2 = s * s;
-    double poly = fma(s2, k.c7, k.c5);
-    poly = fma(s2, poly, k.c3);
-    poly = fma(s2, poly, 2.0);
-    return s * poly;
-}
 
 // Downward merge walk over the pressure-ascending source nodes of one pair of
 // variables (interp_extrap_1d in 'constant' mode, functions.py:511-580).
@@ -160,62 +39,26 @@ struct Walk2 {
     float a_m0, a_m1, b_m0, b_m1;     // raw slabs of node lo-2 (loads issued two advances ahead)
 };
 
-struct Tslab32 { const float *lo, *hi; float w; };
-
 constexpr int kRing = 5;     // levels in flight per thread (cp.async ring, +1 spare slot)
-constexpr int kL2Ahead = 6;  // delta nodes pulled into L2 this many advances ahead of their use
 
-// Two flavours share this body:
-//  * TMA = false: every thread fetches its own column with 4-byte cp.async copies (any ncol,
-//    any alignment) and stores with st.global.cs;
-//  * TMA = true (ncol % 4 == 0, 16-byte aligned fields): a fifth warp streams level PAIRS of the
-//    CTA's 128 columns through a ring of shared-memory slots with cp.async.bulk.tensor (TMA);
-//    the four column warps compute in place in the slot and the producer stores it with TMA.
-//    Handshake per slot: full[s] (TMA bytes landed) and done[s] (all 128 column threads have
-//    written their results back and fenced them for the async proxy).
-template <int NT, bool FAST, bool TMA>
-__global__ void __launch_bounds__(NT + (TMA ? 32 : 0), 3)
-pgw_column_kernel(const __grid_constant__ pgw_timestep_args a,
-                  const __grid_constant__ std::conditional_t<TMA, TmaParams, int> tp,
-                  const int lst, const int np) {
-    extern __shared__ __align__(1024) unsigned char smem[];
-    static_assert(!TMA || NT == 128, "the TMA box is 128 columns wide");
+template <int NT, bool FAST>
+__global__ void __launch_bounds__(NT, 3)
+pgw_column_kernel(const __grid_constant__ pgw_timestep_args a, const int lst, const int np) {
+    extern __shared__ __align__(16) unsigned char smem[];
     const int L = a.nlev, K = a.nplev;
     // ---- shared memory carve-up
-    // generic: (ak,bk)[L+1] | stash | cp.async ring | (akm,bkm)[L] | plev tables
-    // TMA:     pair ring [kTmaSlots][4][2][NT] | stash | (ak,bk)[np+1] | (akm,bkm)[np] | plev tables | barriers
-    double2 *s_hl;      // indexed by the level: (ak, bk) of half level l (TMA: only l >= lst)
-    float2 *st_Te;      // [np][NT] (T_pgw rounded to fp32, e_pgw)
-    float *ring;
-    float2 *s_m;        // indexed by the level: (akm, bkm) of full level l (TMA: only l >= lst)
-    float *s_plev;      // [K] ascending
-    uint64_t *bar_full = nullptr, *bar_done = nullptr;
-    if constexpr (TMA) {
-        ring = reinterpret_cast<float *>(smem);
-        st_Te = reinterpret_cast<float2 *>(ring + kTmaSlots * 8 * NT);
-        double2 *hl0 = reinterpret_cast<double2 *>(st_Te + (size_t)np * NT);
-        float2 *m0 = reinterpret_cast<float2 *>(hl0 + (np + 1));
-        s_plev = reinterpret_cast<float *>(m0 + np);
-        bar_full = reinterpret_cast<uint64_t *>(s_plev + 3 * K + ((3 * K) & 1));
-        bar_done = bar_full + kTmaSlots;
-        s_hl = hl0 - lst;
-        s_m = m0 - lst;
-    } else {
-        s_hl = reinterpret_cast<double2 *>(smem);
-        st_Te = reinterpret_cast<float2 *>(s_hl + (L + 1));
-        ring = reinterpret_cast<float *>(st_Te + (size_t)np * NT);
-        s_m = reinterpret_cast<float2 *>(ring + (size_t)(kRing + 1) * 4 * NT);
-        s_plev = reinterpret_cast<float *>(s_m + L);
-    }
+    double2 *s_hl = reinterpret_cast<double2 *>(smem);                  // [L+1] (ak, bk)
+    float2 *st_Te = reinterpret_cast<float2 *>(s_hl + (L + 1));         // [np][NT] (T_pgw rounded to fp32, e_pgw)
+    float *ring = reinterpret_cast<float *>(st_Te + (size_t)np * NT);   // [kRing+1][4][NT]
+    float2 *s_m = reinterpret_cast<float2 *>(ring + (size_t)(kRing + 1) * 4 * NT);   // [L] (akm, bkm)
+    float *s_plev = reinterpret_cast<float *>(s_m + L);                 // [K] ascending
     float *s_inv_plev = s_plev + K;                                     // [K]
     float *s_inv_w = s_inv_plev + K;                                    // [K] 1/log2(p[j+1]/p[j])
 
     const int tid = threadIdx.x;
-    const int nthr = NT + (TMA ? 32 : 0);
-    const int tab0 = TMA ? lst : 0;
-    for (int i = tab0 + tid; i <= L; i += nthr) s_hl[i] = make_double2(a.ak[i], a.bk[i]);
-    for (int i = tab0 + tid; i < L; i += nthr) s_m[i] = make_float2((float)a.akm[i], (float)a.bkm[i]);
-    for (int i = tid; i < K; i += nthr) {
+    for (int i = tid; i <= L; i += NT) s_hl[i] = make_double2(a.ak[i], a.bk[i]);
+    for (int i = tid; i < L; i += NT) s_m[i] = make_float2((float)a.akm[i], (float)a.bkm[i]);
+    for (int i = tid; i < K; i += NT) {
         const int f0 = a.plev_descending ? (K - 1 - i) : i;
         const float p0 = (float)a.plev[f0];
         s_plev[i] = p0;
@@ -225,66 +68,16 @@ pgw_column_kernel(const __grid_constant__ pgw_timestep_args a,
             s_inv_w[i] = 1.0f / log2f(p1 / p0);
         } else s_inv_w[i] = 0.0f;
     }
-    if constexpr (TMA) {
-        if (tid == 0) {
-            for (int i = 0; i < kTmaSlots; ++i) { mbar_init(bar_full + i, 1); mbar_init(bar_done + i, NT); }
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-    }
     __syncthreads();
 
     const uint32_t n = (uint32_t)a.ncol;
-    const int npairs = (L + 1) >> 1, np1 = np >> 1;    // TMA: level pairs in total / below the stash top
-    if constexpr (TMA) {
-        // ------------------------------------------------------------------ producer warp
-        if (tid >= NT) {
-            if (tid != NT) return;
-            const int c0 = (int)(blockIdx.x * NT);
-            // pair j = levels L-1-2j (row 1) and L-2-2j (row 0).  TMA coordinates must not be negative,
-            // so the last pair of an odd column is levels (1, 0): level 1 is simply done twice.
-            auto pair_row = [&](int j) { const int r = L - 2 - 2 * j; return r < 0 ? 0 : r; };
-            auto load_pair_slot = [&](int j) {
-                const int s = j & (kTmaSlots - 1);
-                float *dst = ring + s * 8 * NT;
-                mbar_arrive_expect_tx(bar_full + s, 4u * 2u * NT * sizeof(float));
-#pragma unroll
-                for (int v = 0; v < 4; ++v) tma_load_2d(dst + v * 2 * NT, &tp.in[v], c0, pair_row(j), bar_full + s);
-            };
-            auto l2_pair = [&](int j) {
-                if (j < npairs) {
-#pragma unroll
-                    for (int v = 0; v < 4; ++v) tma_prefetch_2d(&tp.in[v], c0, pair_row(j));
-                }
-            };
-            for (int j = 0; j < kTmaSlots && j < npairs; ++j) load_pair_slot(j);
-            for (int j = kTmaSlots; j < kTmaSlots + kTmaL2Ahead; ++j) l2_pair(j);
-            for (int j = 0; j < npairs; ++j) {
-                const int s = j & (kTmaSlots - 1);
-                const float *src = ring + s * 8 * NT;
-                mbar_wait(bar_done + s, (j / kTmaSlots) & 1);
-                const int row = pair_row(j);
-                tma_store_2d(&tp.out[0], c0, row, src);
-                if (j >= np1) tma_store_2d(&tp.out[1], c0, row, src + 2 * NT);   // QV of the stash levels: phase 3
-                tma_store_2d(&tp.out[2], c0, row, src + 4 * NT);
-                tma_store_2d(&tp.out[3], c0, row, src + 6 * NT);
-                tma_commit();
-                tma_wait_read<1>();                     // the stores of pair j-1 have left shared memory
-                if (j >= 1 && j - 1 + kTmaSlots < npairs) load_pair_slot(j - 1 + kTmaSlots);
-                l2_pair(j + kTmaSlots + kTmaL2Ahead);
-            }
-            tma_wait_all();
-            return;
-        }
-    }
-    const uint32_t c_raw = blockIdx.x * NT + tid;
-    // Threads past the last column mirror column n-1.  Generic flavour: they compute and store
-    // exactly the same values to the same addresses, which keeps the kernel free of tail branches.
-    // TMA flavour: their slot columns are zero-filled, so their per-thread stores are masked.
-    const uint32_t c = (c_raw >= n) ? n - 1 : c_raw;
-    const bool valid = TMA ? (c_raw < n) : true;
+    uint32_t c = blockIdx.x * NT + tid;
+    // Threads past the last column mirror column n-1: they compute and store exactly the
+    // same values to the same addresses, which keeps the whole kernel free of tail branches.
+    if (c >= n) c = n - 1;
     unsigned errbits = 0;
 
-    // ---- generic flavour, async ring: this thread's T, QV, U, V of one level per slot
+    // ---- async ring: this thread's T, QV, U, V of one level per slot
     const float *gT = a.T, *gQ = a.QV, *gU = a.U, *gV = a.V;
     float *oT = a.T_out, *oQ = a.QV_out, *oU = a.U_out, *oV = a.V_out;
     float *const my_ring = ring + tid;
@@ -305,10 +98,8 @@ pgw_column_kernel(const __grid_constant__ pgw_timestep_args a,
         --lev_w; off_w -= n;
         slot_w = (slot_w == kRing) ? 0 : slot_w + 1;
     };
-    if constexpr (!TMA) {
 #pragma unroll
-        for (int i = 0; i < kRing; ++i) prefetch();
-    }
+    for (int i = 0; i < kRing; ++i) prefetch();
     int slot_r = 0;                                  // slot the next level is read from
 
     // ---------------- surface, skin and soil (step_03:103-146) ----------------
@@ -332,38 +123,35 @@ pgw_column_kernel(const __grid_constant__ pgw_timestep_args a,
             comb = (double)fr * dts + (double)(1.0f - fr) * dtos;
         }
         const double clim = (double)r_clim;
-        if (valid) {
-            a.FR_SEA_ICE_out[c] = sic;
-            a.T_SKIN_out[c] = (float)((double)r_skin + comb);
-        }
+        a.FR_SEA_ICE_out[c] = sic;
+        a.T_SKIN_out[c] = (float)((double)r_skin + comb);
         for (int s = 0; s < a.nsoil; ++s) {
             const double dso = clim + a.soil_decay[s] * (comb - clim);
-            const float so = (float)((double)__ldg(a.T_SO + (uint32_t)s * n + c) + dso);
-            if (valid) a.T_SO_out[(uint32_t)s * n + c] = so;
+            a.T_SO_out[(uint32_t)s * n + c] = (float)((double)__ldg(a.T_SO + (uint32_t)s * n + c) + dso);
         }
     }
 
     // ---------------- delta walkers (functions.py:343-431) ----------------
-    const auto tw = [](const pgw_tslab &s) { return (s.x_new == 0.0) ? 0.0f : (float)(s.x_new / s.x_hi); };
-    const Tslab32 v_ta{a.ta.lo, a.ta.hi, tw(a.ta)}, v_hur{a.hur.lo, a.hur.hi, tw(a.hur)};
-    const Tslab32 v_ua{a.ua.lo, a.ua.hi, tw(a.ua)}, v_va{a.va.lo, a.va.hi, tw(a.va)};
+    // The 3-D deltas are packed per node and column as float4 (ta, hur, ua, va): walker A reads the
+    // .xy half, walker B the .zw half (`pair` = 0 / 1), one 8-byte load per time slab.
+    const float w_t = slab_weight(a.d4);
+    const float2 *const d4lo = reinterpret_cast<const float2 *>(a.d4.lo);
+    const float2 *const d4hi = reinterpret_cast<const float2 *>(a.d4.hi);
     const int desc = a.plev_descending;
     // raw loads of node j of a variable pair (time slabs lo/hi); blended when consumed
-    auto load_raw = [&](const Tslab32 &va, const Tslab32 &vb, int j, float &a0, float &a1, float &b0, float &b1) {
-        const uint32_t off = (uint32_t)(desc ? (K - 1 - j) : j) * n + c;
-        a0 = __ldg(va.lo + off); a1 = __ldg(va.hi + off);
-        b0 = __ldg(vb.lo + off); b1 = __ldg(vb.hi + off);
+    auto load_raw = [&](int pair, int j, float &a0, float &a1, float &b0, float &b1) {
+        const uint32_t off = ((uint32_t)(desc ? (K - 1 - j) : j) * n + c) * 2u + pair;
+        const float2 x0 = __ldg(d4lo + off), x1 = __ldg(d4hi + off);
+        a0 = x0.x; b0 = x0.y; a1 = x1.x; b1 = x1.y;
     };
-    auto blend = [](float w, float x0, float x1) { return (w == 0.0f) ? x0 : fmaf(w, x1 - x0, x0); };
+    auto blend = [&](float x0, float x1) { return blend_f32(w_t, x0, x1); };
     // The register prefetch above covers two advances (~2 levels of work), less than a DRAM
     // round trip under load; the lines of node j are therefore pulled into L2 kL2Ahead
     // advances ahead, which costs neither registers nor shared memory.
-    auto l2_prefetch = [&](const Tslab32 &va, const Tslab32 &vb, int j) {
-        const uint32_t off = (uint32_t)(desc ? (K - 1 - j) : j) * n + c;
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(va.lo + off));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(va.hi + off));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(vb.lo + off));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(vb.hi + off));
+    auto l2_prefetch = [&](int pair, int j) {
+        const uint32_t off = ((uint32_t)(desc ? (K - 1 - j) : j) * n + c) * 2u + pair;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(d4lo + off));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(d4hi + off));
     };
 
     Walk2 wA, wB;
@@ -383,21 +171,21 @@ pgw_column_kernel(const __grid_constant__ pgw_timestep_args a,
         wA.b_lo = (float)blend_f64(a.hurs, r_hurs); wA.b_d = 0.0f;
         wA.a_n0 = wA.a_n1 = wA.b_n0 = wA.b_n1 = 0.0f;
         wA.a_m0 = wA.a_m1 = wA.b_m0 = wA.b_m1 = 0.0f;
-        if (s >= 1) load_raw(v_ta, v_hur, s - 1, wA.a_n0, wA.a_n1, wA.b_n0, wA.b_n1);
-        if (s >= 2) load_raw(v_ta, v_hur, s - 2, wA.a_m0, wA.a_m1, wA.b_m0, wA.b_m1);
+        if (s >= 1) load_raw(0, s - 1, wA.a_n0, wA.a_n1, wA.b_n0, wA.b_n1);
+        if (s >= 2) load_raw(0, s - 2, wA.a_m0, wA.a_m1, wA.b_m0, wA.b_m1);
 
         float x0, x1, y0, y1;
-        load_raw(v_ua, v_va, K - 1, x0, x1, y0, y1);
+        load_raw(1, K - 1, x0, x1, y0, y1);
         wB.lo = K - 1; wB.p_lo = s_plev[K - 1]; wB.inv_p_lo = s_inv_plev[K - 1]; wB.inv_w = 0.0f;
-        wB.a_lo = blend(v_ua.w, x0, x1); wB.a_d = 0.0f;
-        wB.b_lo = blend(v_va.w, y0, y1); wB.b_d = 0.0f;
-        load_raw(v_ua, v_va, K - 2, wB.a_n0, wB.a_n1, wB.b_n0, wB.b_n1);
+        wB.a_lo = blend(x0, x1); wB.a_d = 0.0f;
+        wB.b_lo = blend(y0, y1); wB.b_d = 0.0f;
+        load_raw(1, K - 2, wB.a_n0, wB.a_n1, wB.b_n0, wB.b_n1);
         wB.a_m0 = wB.a_m1 = wB.b_m0 = wB.b_m1 = 0.0f;
-        if (K >= 3) load_raw(v_ua, v_va, K - 3, wB.a_m0, wB.a_m1, wB.b_m0, wB.b_m1);
+        if (K >= 3) load_raw(1, K - 3, wB.a_m0, wB.a_m1, wB.b_m0, wB.b_m1);
 #pragma unroll
         for (int d = 3; d <= kL2Ahead; ++d) {
-            if (s - d >= 0) l2_prefetch(v_ta, v_hur, s - d);
-            if (K - 1 - d >= 0) l2_prefetch(v_ua, v_va, K - 1 - d);
+            if (s - d >= 0) l2_prefetch(0, s - d);
+            if (K - 1 - d >= 0) l2_prefetch(1, K - 1 - d);
         }
     }
     float min_src_p = (wA.lo == 0) ? wA.p_lo : s_plev[0];
@@ -407,13 +195,13 @@ pgw_column_kernel(const __grid_constant__ pgw_timestep_args a,
     // (which waits for loads issued one step, i.e. several levels, ago) before ANY new load is
     // issued.  Issued the other way round, the second walker's register reads wait on the
     // scoreboard of the first walker's brand-new loads: a full DRAM round trip per step.
-    auto step_consume = [&](Walk2 &w, const Tslab32 &va, const Tslab32 &vb) {
+    auto step_consume = [&](Walk2 &w) {
         const float hi_p = w.p_lo, hi_a = w.a_lo, hi_b = w.b_lo;
         const bool from_synth = (hi_p != s_plev[w.lo]);     // leaving the (ps_hist, sfc) node
         --w.lo;
         if (w.lo >= 0) {
             w.p_lo = s_plev[w.lo]; w.inv_p_lo = s_inv_plev[w.lo];
-            w.a_lo = blend(va.w, w.a_n0, w.a_n1); w.b_lo = blend(vb.w, w.b_n0, w.b_n1);
+            w.a_lo = blend(w.a_n0, w.a_n1); w.b_lo = blend(w.b_n0, w.b_n1);
             w.a_d = hi_a - w.a_lo; w.b_d = hi_b - w.b_lo;
             w.inv_w = from_synth ? fast_rcp(fast_lg2(hi_p * w.inv_p_lo)) : s_inv_w[w.lo];
             w.a_n0 = w.a_m0; w.a_n1 = w.a_m1; w.b_n0 = w.b_m0; w.b_n1 = w.b_m1;
@@ -423,27 +211,19 @@ pgw_column_kernel(const __grid_constant__ pgw_timestep_args a,
         }
     };
     // `zero` (== 0) carries a data dependency on the registers consumed above
-    auto step_load = [&](Walk2 &w, const Tslab32 &va, const Tslab32 &vb, int zero) {
-        if (w.lo >= 2) load_raw(va, vb, w.lo - 2 + zero, w.a_m0, w.a_m1, w.b_m0, w.b_m1);
-        if (w.lo >= kL2Ahead) l2_prefetch(va, vb, w.lo - kL2Ahead);
-    };
-    auto reg_fence = [](float x0, float x1, float x2, float x3) {
-        int z;
-        asm volatile("{\n\t.reg .b32 t;\n\tor.b32 t, %1, %2;\n\tor.b32 t, t, %3;\n\tor.b32 t, t, %4;\n\t"
-                     "and.b32 %0, t, 0;\n\t}"
-                     : "=r"(z) : "r"(__float_as_int(x0)), "r"(__float_as_int(x1)), "r"(__float_as_int(x2)),
-                       "r"(__float_as_int(x3)));
-        return z;
+    auto step_load = [&](Walk2 &w, int pair, int zero) {
+        if (w.lo >= 2) load_raw(pair, w.lo - 2 + zero, w.a_m0, w.a_m1, w.b_m0, w.b_m1);
+        if (w.lo >= kL2Ahead) l2_prefetch(pair, w.lo - kL2Ahead);
     };
     // advance both walkers until p_lo <= p (or the first node has been passed)
     auto advance = [&](float p) {
         do {
             const bool sa = wA.p_lo > p, sb = wB.p_lo > p;
-            if (sa) step_consume(wA, v_ta, v_hur);
-            if (sb) step_consume(wB, v_ua, v_va);
+            if (sa) step_consume(wA);
+            if (sb) step_consume(wB);
             const int zero = reg_fence(wA.a_n1, wA.b_n1, wB.a_n1, wB.b_n1);
-            if (sa) step_load(wA, v_ta, v_hur, zero);
-            if (sb) step_load(wB, v_ua, v_va, zero);
+            if (sa) step_load(wA, 0, zero);
+            if (sb) step_load(wB, 1, zero);
         } while (fmaxf(wA.p_lo, wB.p_lo) > p);
     };
 
@@ -458,7 +238,7 @@ pgw_column_kernel(const __grid_constant__ pgw_timestep_args a,
     if (!era_open) errbits |= PGW_ERR_PREF_BELOW_SFC;
     float psn_f = ps_f;                             // ps used for QV; replaced after the iteration
 
-    const auto read_fence = reg_fence;
+    const auto read_fence = [](float x0, float x1, float x2, float x3) { return reg_fence(x0, x1, x2, x3); };
     // The per-level work is split into the (sequential, cheap) walker step and the (independent,
     // expensive) thermodynamics.  The sweeps process levels in PAIRS: both walker steps first,
     // then the thermodynamics of the two levels in one branch-free block so that the two
@@ -477,39 +257,9 @@ pgw_column_kernel(const __grid_constant__ pgw_timestep_args a,
         d.va = (tB == 0.0f) ? wB.b_lo : fmaf(tB, wB.b_d, wB.b_lo);
         return d;
     };
-    // Saturation vapour pressure of the ERA and the PGW state (functions.py:74-105), RELHUM of
-    // the ERA state (:107-116) + delta, back to vapour pressure (:123); T - 273.16 is formed from
-    // the exact T - 273 so that T_pgw is never rounded to fp32.  `cold` (warp-uniform): every
-    // temperature involved is <= 250.16 K, ice only (alpha == 0 exactly).  The general form is
-    // branch free: both exponentials, alpha from selects (exactly 1 / 0 outside the mixed band).
     auto thermo = [&](bool cold, float p, float t, float q, const Dlt &d) -> float {
-        const float tm273 = t - 273.0f;
-        const float dTe = tm273 - 0.16f, tkp = tm273 + d.ta, dTp = tm273 + (d.ta - 0.16f);
-        constexpr float kCw = 17.502f * 1.4426950408889634f, kCi = 22.587f * 1.4426950408889634f;
-        float es_e, es_p;
-        if (cold) {
-            const float de = tm273 + (273.0f + 0.7f), dp = tkp + (273.0f + 0.7f);
-            const float rr = fast_rcp(de * dp);               // one reciprocal for both states
-            es_e = 611.21f * fast_ex2(kCi * dTe * (rr * dp));
-            es_p = 611.21f * fast_ex2(kCi * dTp * (rr * de));
-        } else {
-            const float dew = tm273 + (273.0f - 32.19f), dei = tm273 + (273.0f + 0.7f);
-            const float dpw = tkp + (273.0f - 32.19f), dpi = tkp + (273.0f + 0.7f);
-            const float pe = dew * dei, pp = dpw * dpi;
-            const float rr = fast_rcp(pe * pp);               // one reciprocal for all four quotients
-            const float re = rr * pp, rp = rr * pe;           // 1/pe, 1/pp
-            const float ew_e = fast_ex2(kCw * dTe * (re * dei)), ei_e = fast_ex2(kCi * dTe * (re * dew));
-            const float ew_p = fast_ex2(kCw * dTp * (rp * dpi)), ei_p = fast_ex2(kCi * dTp * (rp * dpw));
-            const float r_e = (dTe + 23.0f) * (1.0f / 23.0f), r_p = (dTp + 23.0f) * (1.0f / 23.0f);
-            const float al_e = dTe >= 0.0f ? 1.0f : (dTe <= -23.0f ? 0.0f : r_e * r_e);   // NaN stays NaN
-            const float al_p = dTp >= 0.0f ? 1.0f : (dTp <= -23.0f ? 0.0f : r_p * r_p);
-            es_e = 611.21f * (al_e * ew_e + (1.0f - al_e) * ei_e);
-            es_p = 611.21f * (al_p * ew_p + (1.0f - al_p) * ei_p);
-        }
-        const float rh_pgw = fmaf(100.0f * q * p, fast_rcp((0.622f + 0.378f * q) * es_e), d.hur);
-        return rh_pgw * 0.01f * es_p;
+        return thermo_e_pgw(cold, p, t, q, d.ta, d.hur);
     };
-    auto is_cold = [](float t, float dta) { return fmaxf(t, t + dta) <= 250.0f; };   // conservative
 
     // ---------------- phase 1: surface .. p_ref, parked in shared memory ----------------
     uint32_t off = (uint32_t)(L - 1) * n + c;
@@ -538,32 +288,6 @@ pgw_column_kernel(const __grid_constant__ pgw_timestep_args a,
                 pb_era = pt;
             }
         };
-        if constexpr (TMA) {
-            // np is even here: the stash is exactly np1 pairs
-            for (int j = 0; j < np1; ++j, pTe -= 2 * NT) {
-                const int l = L - 1 - 2 * j;
-                float *sl = ring + (j & (kTmaSlots - 1)) * 8 * NT + tid;
-                mbar_wait(bar_full + (j & (kTmaSlots - 1)), (j / kTmaSlots) & 1);
-                const float t0 = sl[NT], q0 = sl[3 * NT], u0 = sl[5 * NT], v0 = sl[7 * NT];    // row 1: level l
-                const float t1 = sl[0], q1 = sl[2 * NT], u1 = sl[4 * NT], v1 = sl[6 * NT];     // row 0: level l-1
-                const float2 m0 = s_m[l], m1 = s_m[l - 1];
-                const float p0 = fmaf(ps_f, m0.y, m0.x), p1 = fmaf(ps_f, m1.y, m1.x);
-                const Dlt d0 = walk(p0);
-                const Dlt d1 = walk(p1);
-                const bool cold = __all_sync(0xffffffffu, is_cold(t0, d0.ta) && is_cold(t1, d1.ta));
-                const float e0 = thermo(cold, p0, t0, q0, d0), e1 = thermo(cold, p1, t1, q1, d1);
-                const float tp0 = t0 + d0.ta, tp1 = t1 + d1.ta;
-                sl[NT] = tp0; sl[5 * NT] = u0 + d0.ua; sl[7 * NT] = v0 + d0.va;
-                sl[0] = tp1; sl[4 * NT] = u1 + d1.ua; sl[6 * NT] = v1 + d1.va;
-                fence_proxy_async();
-                mbar_arrive(bar_done + (j & (kTmaSlots - 1)));
-                pTe[0] = make_float2(tp0, e0);
-                pTe[-NT] = make_float2(tp1, e1);
-                if (j == 0) t_low_d = (double)t0 + (double)d0.ta;
-                era_layer(l, p0, t0, q0, d0.ta, tp0, e0);
-                era_layer(l - 1, p1, t1, q1, d1.ta, tp1, e1);
-            }
-        } else {
         int l = L - 1;
         for (; l - 1 >= lst; l -= 2, off -= 2 * n, pTe -= 2 * NT) {
             __pipeline_wait_prior(kRing - 2);
@@ -606,7 +330,6 @@ pgw_column_kernel(const __grid_constant__ pgw_timestep_args a,
             era_layer(l, p0, t0, q0, d0.ta, tp0, e0);
             off -= n;
         }
-        }
     }
     const double fis = (double)r_fis;
     const double phi_era = fis + kRd * acc_era;
@@ -623,7 +346,7 @@ pgw_column_kernel(const __grid_constant__ pgw_timestep_args a,
         dps += adj;
         psn = PSd + dps;
         psn_f = (float)psn;
-        if (valid) *traj = (float)dps;
+        *traj = (float)dps;
         if (psn > a.ps_bound) errbits |= PGW_ERR_PS_BOUND;
         double pb = fma(psn, hl_sfc.y, hl_sfc.x);
         if (pb < pref) errbits |= PGW_ERR_PREF_BELOW_SFC;
@@ -663,7 +386,7 @@ pgw_column_kernel(const __grid_constant__ pgw_timestep_args a,
         const double phi_pgw = fis + kRd * acc;
         const double err = (phi_pgw - phi_era) - gdzg;
         adj = -a.adj_factor * psn / (kRd * t_low) * err;
-        double ae = (isnan(err) || !valid) ? 0.0 : fabs(err);                  // max skips NaN (step_03:308)
+        double ae = isnan(err) ? 0.0 : fabs(err);                  // max skips NaN (step_03:308)
         ae = warp_max(ae);
         if ((tid & 31) == 0 && ae > 0.0)
             atomicMax(reinterpret_cast<unsigned long long *>(a.maxerr + k),
@@ -671,43 +394,21 @@ pgw_column_kernel(const __grid_constant__ pgw_timestep_args a,
     }
 
     // ---------------- phase 3: PS, QV of the parked levels, then the upper column ----------------
-    if (valid) {
-        a.PS_out[c] = psn_f;
-        a.dps_out[c] = (float)dps;
-    }
+    a.PS_out[c] = psn_f;
+    a.dps_out[c] = (float)dps;
     {
         const float2 *pTe = bTe;
         uint32_t o2 = (uint32_t)(L - 1) * n + c;
         for (int l = L - 1; l >= lst; --l, pTe -= NT, o2 -= n) {
             const float2 m = s_m[l];
             const float e = pTe->y;
-            const float qv = 0.622f * e * fast_rcp(fmaf(-0.378f, e, fmaf(psn_f, m.y, m.x)));
-            if (valid) st_stream(oQ + o2, qv);
+            st_stream(oQ + o2, 0.622f * e * fast_rcp(fmaf(-0.378f, e, fmaf(psn_f, m.y, m.x))));
         }
     }
     {
         auto qv_of = [&](float e, float2 m) {     // functions.py:66-72 with the adjusted ps
             return 0.622f * e * fast_rcp(fmaf(-0.378f, e, fmaf(psn_f, m.y, m.x)));
         };
-        if constexpr (TMA) {
-            for (int j = np1; j < npairs; ++j) {
-                const int l = max(L - 1 - 2 * j, 1);          // last pair of an odd column: levels (1, 0) again
-                float *sl = ring + (j & (kTmaSlots - 1)) * 8 * NT + tid;
-                const float2 m0 = tp.m[l], m1 = tp.m[l - 1];
-                mbar_wait(bar_full + (j & (kTmaSlots - 1)), (j / kTmaSlots) & 1);
-                const float t0 = sl[NT], q0 = sl[3 * NT], u0 = sl[5 * NT], v0 = sl[7 * NT];
-                const float t1 = sl[0], q1 = sl[2 * NT], u1 = sl[4 * NT], v1 = sl[6 * NT];
-                const float p0 = fmaf(ps_f, m0.y, m0.x), p1 = fmaf(ps_f, m1.y, m1.x);
-                const Dlt d0 = walk(p0);
-                const Dlt d1 = walk(p1);
-                const bool cold = __all_sync(0xffffffffu, is_cold(t0, d0.ta) && is_cold(t1, d1.ta));
-                const float e0 = thermo(cold, p0, t0, q0, d0), e1 = thermo(cold, p1, t1, q1, d1);
-                sl[NT] = t0 + d0.ta; sl[3 * NT] = qv_of(e0, m0); sl[5 * NT] = u0 + d0.ua; sl[7 * NT] = v0 + d0.va;
-                sl[0] = t1 + d1.ta; sl[2 * NT] = qv_of(e1, m1); sl[4 * NT] = u1 + d1.ua; sl[6 * NT] = v1 + d1.va;
-                fence_proxy_async();
-                mbar_arrive(bar_done + (j & (kTmaSlots - 1)));
-            }
-        } else {
         int l = lst - 1;
         for (; l - 1 >= 0; l -= 2, off -= 2 * n) {
             __pipeline_wait_prior(kRing - 2);
@@ -743,21 +444,18 @@ pgw_column_kernel(const __grid_constant__ pgw_timestep_args a,
             st_stream(oQ + off, qv_of(e0, m0));
             off -= n;
         }
-        __pipeline_wait_prior(0);
-        }
     }
+    __pipeline_wait_prior(0);
 
     // ---------------- bookkeeping for the host-side checks ----------------
-    float2 m_top;
-    if constexpr (TMA) m_top = tp.m[0]; else m_top = s_m[0];
-    float p_top = fmaf(ps_f, m_top.y, m_top.x);                          // functions.py:417
+    float p_top = fmaf(ps_f, s_m[0].y, s_m[0].x);                        // functions.py:417
     p_top = warp_min(p_top);
     min_src_p = warp_min(min_src_p);
     if ((tid & 31) == 0) {
         atomicMin(reinterpret_cast<unsigned *>(a.stats), __float_as_uint(fmaxf(p_top, 0.0f)));
         atomicMin(reinterpret_cast<unsigned *>(a.stats) + 1, __float_as_uint(fmaxf(min_src_p, 0.0f)));
     }
-    if (errbits && valid) atomicOr(a.err, errbits);
+    if (errbits) atomicOr(a.err, errbits);
 }
 
 __global__ void pgw_timestep_init_kernel(uint64_t *maxerr, float *stats) {
@@ -815,7 +513,7 @@ pgw_rewrite_kernel(const __grid_constant__ pgw_timestep_args a, const pgw_timest
 // ---------------------------------------------------------------------------
 namespace {
 
-constexpr int kColumnThreads = 128;
+using pgw::kColumnThreads;
 
 // First (topmost) full level whose layer can reach p_ref for any ps <= ps_bound:
 // the layer above the first half level with ak + ps_bound*bk >= p_ref.
@@ -839,116 +537,52 @@ size_t column_smem(int nlev, int nplev, int np, int nt) {
 int validate(const pgw_timestep_args *a) {
     if (!a) return PGW_E_INVALID;
     if (a->ncol <= 0 || a->nlev < 2 || a->nplev < 2 || a->nplev > 64) return PGW_E_INVALID;
-    // 32-bit element offsets inside the kernel
+    // 32-bit element offsets inside the kernels (the packed deltas hold 4 floats per node and column)
     if ((unsigned long long)a->ncol * (unsigned long long)(a->nlev + 1) >= (1ull << 30)) return PGW_E_INVALID;
+    if ((unsigned long long)a->ncol * (unsigned long long)a->nplev >= (1ull << 29)) return PGW_E_INVALID;
     if (a->nsoil < 0 || a->nsoil > PGW_MAX_SOIL) return PGW_E_INVALID;
     if (a->k_spec < 1 || a->k_spec > PGW_MAX_ITER) return PGW_E_INVALID;
     const void *need[] = {a->ak_host, a->bk_host, a->ak, a->bk, a->akm, a->bkm, a->plev, a->PS, a->FIS, a->FR_LAND, a->FR_SEA_ICE,
-                          a->T_SKIN, a->T, a->QV, a->U, a->V, a->ta.lo, a->ta.hi, a->hur.lo, a->hur.hi,
-                          a->ua.lo, a->ua.hi, a->va.lo, a->va.hi, a->tas.lo, a->tas.hi, a->hurs.lo,
+                          a->T_SKIN, a->T, a->QV, a->U, a->V, a->d4.lo, a->d4.hi, a->tas.lo, a->tas.hi, a->hurs.lo,
                           a->hurs.hi, a->ps_hist.lo, a->ps_hist.hi, a->ts.lo, a->ts.hi, a->tos.lo, a->tos.hi,
                           a->siconc.lo, a->siconc.hi, a->zg_ref.lo, a->zg_ref.hi, a->ts_clim, a->PS_out,
                           a->T_SKIN_out, a->FR_SEA_ICE_out, a->T_out, a->QV_out, a->U_out, a->V_out,
                           a->dps_out, a->dps_traj, a->maxerr, a->stats, a->err};
     for (const void *p : need) if (!p) return PGW_E_INVALID;
+    if ((reinterpret_cast<uintptr_t>(a->d4.lo) | reinterpret_cast<uintptr_t>(a->d4.hi)) & 15u) return PGW_E_INVALID;
     if (a->nsoil > 0 && (!a->T_SO || !a->T_SO_out)) return PGW_E_INVALID;
     return PGW_OK;
 }
 
-
-// ---- TMA flavour: eligibility, shared memory, tensor maps
-struct ColumnPlan {
-    bool tma;
-    int lst, np;
-    size_t smem;
-};
-
-size_t column_smem_tma(int nplev, int np, int nt) {
-    size_t b = sizeof(float) * (size_t)pgw::kTmaSlots * 8 * nt +            // pair ring
-               (size_t)np * nt * (2 * sizeof(float)) +                      // stash
-               sizeof(double) * 2 * (size_t)(np + 1) + sizeof(float) * 2 * (size_t)np;
-    b += sizeof(float) * (size_t)(3 * nplev + ((3 * nplev) & 1));
-    b += sizeof(uint64_t) * 2 * pgw::kTmaSlots;
-    return b;
-}
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
-                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
-                                  CUtensorMapFloatOOBfill);
-
-EncodeTiledFn encode_tiled() {
-    static EncodeTiledFn fn = []() -> EncodeTiledFn {
-        void *p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
-            q != cudaDriverEntryPointSuccess)
-            p = nullptr;
-        cudaGetLastError();
-        return reinterpret_cast<EncodeTiledFn>(p);
-    }();
-    return fn;
-}
-
-bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
-
-// PGW_COLUMN_PATH=generic forces the cp.async flavour (parity tests run both)
+// PGW_COLUMN_PATH=generic forces the cp.async flavour (the parity tests run both)
 bool tma_allowed() {
     const char *e = getenv("PGW_COLUMN_PATH");
     return !(e && strcmp(e, "generic") == 0);
 }
 
-ColumnPlan plan_column(const pgw_timestep_args *a) {
-    ColumnPlan p;
+pgw_column_plan plan_column(const pgw_timestep_args *a) {
+    pgw_column_plan p;
     p.lst = stash_top(a->ak_host, a->bk_host, a->nlev, a->p_ref, a->ps_bound);
     p.np = a->nlev - p.lst;
     p.smem = column_smem(a->nlev, a->nplev, p.np, kColumnThreads);
     p.tma = false;
-    const int lst_even = p.lst - (p.np & 1);            // the TMA flavour parks whole level pairs
-    if (tma_allowed() && a->akm_host && a->bkm_host && lst_even >= 0 && a->nlev <= pgw::kTmaMaxLev &&
-        a->ncol % 4 == 0 && a->ncol >= kColumnThreads && a->ncol < (1ll << 31) &&
-        aligned16(a->T) && aligned16(a->QV) && aligned16(a->U) &&
-        aligned16(a->V) && aligned16(a->T_out) && aligned16(a->QV_out) && aligned16(a->U_out) &&
-        aligned16(a->V_out) && encode_tiled()) {
+    int lst_tma = 0;
+    size_t smem_tma = 0;
+    if (tma_allowed() && pgw_tma_eligible(a, p.lst, &lst_tma, &smem_tma)) {
         p.tma = true;
-        p.lst = lst_even;
-        p.np = a->nlev - lst_even;
-        p.smem = column_smem_tma(a->nplev, p.np, kColumnThreads);
+        p.lst = lst_tma;
+        p.np = a->nlev - lst_tma;
+        p.smem = smem_tma;
     }
+    // FAST: every layer the iteration can touch has s = (pb-pt)/(pb+pt) < 0.06 for all ps in
+    // [p_ref, ps_bound] (s is monotone in ps), so the series needs no exact-log fallback.
+    p.fast = true;
+    for (int l = p.lst; l < a->nlev; ++l)
+        for (double ps : {a->p_ref, a->ps_bound}) {
+            const double pt = a->ak_host[l] + ps * a->bk_host[l], pb = a->ak_host[l + 1] + ps * a->bk_host[l + 1];
+            if (!(pt > 0.0) || !((pb - pt) / (pb + pt) < 0.055)) p.fast = false;
+        }
     return p;
-}
-
-int make_map(CUtensorMap *m, const float *base, long long ncol, int nlev) {
-    const cuuint64_t dims[2] = {(cuuint64_t)ncol, (cuuint64_t)nlev};
-    const cuuint64_t strides[1] = {(cuuint64_t)ncol * sizeof(float)};
-    const cuuint32_t box[2] = {(cuuint32_t)kColumnThreads, 2u};
-    const cuuint32_t estr[2] = {1u, 1u};
-    CUresult r = encode_tiled()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box,
-                                estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-        pgw_set_error("cuTensorMapEncodeTiled failed (%d)", (int)r);
-        return PGW_E_LAUNCH;
-    }
-    return PGW_OK;
-}
-
-template <typename Kern>
-int configure_smem(Kern kern, size_t smem, int np, size_t &conf) {
-    if (smem <= conf) return PGW_OK;
-    int dev = 0, max_optin = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    if (smem > (size_t)max_optin) {
-        pgw_set_error("column stash needs %zu B of shared memory (%d levels below p_ref), device allows %d",
-                      smem, np, max_optin);
-        return PGW_E_SMEM;
-    }
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-        return pgw_check_launch("cudaFuncSetAttribute");
-    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    conf = smem;
-    return PGW_OK;
 }
 
 }  // namespace
@@ -961,7 +595,6 @@ long long pgw_timestep_smem_bytes(const pgw_timestep_args *a) {
     return (long long)plan_column(a).smem;
 }
 
-/* 1 if pgw_timestep() would take the TMA flavour of the column kernel for these args */
 int pgw_timestep_uses_tma(const pgw_timestep_args *a) {
     int rc = validate(a);
     if (rc != PGW_OK) return rc;
@@ -972,40 +605,30 @@ int pgw_timestep(const pgw_timestep_args *a, void *stream) {
     int rc = validate(a);
     if (rc != PGW_OK) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    const ColumnPlan plan = plan_column(a);
-    const int lst = plan.lst, np = plan.np;
-    // FAST: every layer the iteration can touch has s = (pb-pt)/(pb+pt) < 0.06 for all ps in
-    // [p_ref, ps_bound] (s is monotone in ps), so the series needs no exact-log fallback.
-    bool fast = true;
-    for (int l = lst; l < a->nlev; ++l)
-        for (double ps : {a->p_ref, a->ps_bound}) {
-            const double pt = a->ak_host[l] + ps * a->bk_host[l], pb = a->ak_host[l + 1] + ps * a->bk_host[l + 1];
-            if (!(pt > 0.0) || !((pb - pt) / (pb + pt) < 0.055)) fast = false;
-        }
-    static thread_local size_t configured[4] = {0, 0, 0, 0};
-    const unsigned grid = (unsigned)((a->ncol + kColumnThreads - 1) / kColumnThreads);
-    if (plan.tma) {
-        pgw::TmaParams tp;
-        const float *in[4] = {a->T, a->QV, a->U, a->V};
-        float *out[4] = {a->T_out, a->QV_out, a->U_out, a->V_out};
-        for (int v = 0; v < 4; ++v) {
-            if ((rc = make_map(&tp.in[v], in[v], a->ncol, a->nlev)) != PGW_OK) return rc;
-            if ((rc = make_map(&tp.out[v], out[v], a->ncol, a->nlev)) != PGW_OK) return rc;
-        }
-        for (int l = 0; l < pgw::kTmaMaxLev; ++l)
-            tp.m[l] = l < a->nlev ? make_float2((float)a->akm_host[l], (float)a->bkm_host[l]) : make_float2(0.f, 0.f);
-        auto kern = fast ? pgw::pgw_column_kernel<kColumnThreads, true, true>
-                         : pgw::pgw_column_kernel<kColumnThreads, false, true>;
-        if ((rc = configure_smem(kern, plan.smem, np, configured[fast ? 3 : 2])) != PGW_OK) return rc;
-        pgw::pgw_timestep_init_kernel<<<1, 64, 0, st>>>(a->maxerr, a->stats);
-        kern<<<grid, kColumnThreads + 32, plan.smem, st>>>(*a, tp, lst, np);
-        return pgw_check_launch("pgw_column_kernel<tma>");
-    }
-    auto kern = fast ? pgw::pgw_column_kernel<kColumnThreads, true, false>
-                     : pgw::pgw_column_kernel<kColumnThreads, false, false>;
-    if ((rc = configure_smem(kern, plan.smem, np, configured[fast ? 1 : 0])) != PGW_OK) return rc;
+    const pgw_column_plan plan = plan_column(a);
     pgw::pgw_timestep_init_kernel<<<1, 64, 0, st>>>(a->maxerr, a->stats);
-    kern<<<grid, kColumnThreads, plan.smem, st>>>(*a, 0, lst, np);
+    if (plan.tma) return pgw_launch_column_tma(a, plan, st);
+
+    auto kern = plan.fast ? pgw::pgw_column_kernel<kColumnThreads, true> : pgw::pgw_column_kernel<kColumnThreads, false>;
+    static thread_local size_t configured[2] = {0, 0};
+    size_t &conf = configured[plan.fast ? 1 : 0];
+    if (plan.smem > conf) {
+        int dev = 0, max_optin = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        if (plan.smem > (size_t)max_optin) {
+            pgw_set_error("column stash needs %zu B of shared memory (%d levels below p_ref), device allows %d",
+                          plan.smem, plan.np, max_optin);
+            return PGW_E_SMEM;
+        }
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem) != cudaSuccess)
+            return pgw_check_launch("cudaFuncSetAttribute");
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared);
+        conf = plan.smem;
+    }
+    const unsigned grid = (unsigned)((a->ncol + kColumnThreads - 1) / kColumnThreads);
+    kern<<<grid, kColumnThreads, plan.smem, st>>>(*a, plan.lst, plan.np);
     return pgw_check_launch("pgw_column_kernel");
 }
 

@@ -25,6 +25,7 @@ from . import _native as N
 from . import settings, timeinterp
 
 VARS_3D = ("ta", "hur", "ua", "va", "zg")
+VARS_PACKED = ("ta", "hur", "ua", "va")       # one float4 per pressure node and column on the device
 VARS_2D = ("tas", "hurs", "ps_hist", "ts", "tos", "siconc")
 
 _STATUS_BYTES = 8 * N.PGW_MAX_ITER + 16 + 8 + 8     # maxerr | result | stats | err,pad
@@ -54,6 +55,11 @@ class DeltaSet:
     for ta, hur, ua, va, zg, tas, hurs, ts, tos, siconc (SCEN-HIST) and ``ps_hist``
     (the HIST ps climatology, functions.py:330-332).  29 February is dropped
     once here (functions.py:224-230).
+
+    Layout in HBM: ta, hur, ua, va are interleaved per pressure node and column as
+    ``d4[nt, K, ny, nx, 4]`` (one 16-byte load per node, month and column in the column
+    kernel); ``vars[name]["data"]`` of these four are strided views of ``d4``.  zg and
+    the 2-D deltas stay separate, contiguous fields.
     """
 
     def __init__(self, deltas, device="cuda"):
@@ -86,6 +92,13 @@ class DeltaSet:
             raise ValueError("Source pressure values must be ascending!")
         self.plev_descending = desc
         self.plev_dev = torch.as_tensor(plev, device=self.device, dtype=torch.float64)
+        stamps = self.vars["ta"]["time"]
+        for name in ("hur", "ua", "va"):
+            if not np.array_equal(self.vars[name]["time"], stamps):
+                raise ValueError("ta, hur, ua, va deltas must share their time stamps")
+        self.d4 = torch.stack([self.vars[n]["data"] for n in VARS_PACKED], dim=-1).contiguous()
+        for i, name in enumerate(VARS_PACKED):
+            self.vars[name]["data"] = self.d4[..., i]
         self._brackets = {}
         self.ts_clim = None
         self.refresh_derived()
@@ -99,7 +112,7 @@ class DeltaSet:
 
     def tensors(self):
         """All device tensors in a fixed order (for the NCCL broadcast)."""
-        return [self.vars[n]["data"] for n in VARS_3D + VARS_2D]
+        return [self.d4] + [self.vars[n]["data"] for n in ("zg",) + VARS_2D]
 
     def bracket(self, name, when):
         key = (name, when)
@@ -119,6 +132,11 @@ class DeltaSet:
         if level is not None:
             lo, hi = lo[level], hi[level]
         return N.TSlab(lo.data_ptr(), hi.data_ptr(), b.x_hi, b.x_new)
+
+    def slab4(self, when):
+        """pgw_tslab of the packed (ta, hur, ua, va) deltas at ERA5 time ``when``."""
+        b = self.bracket("ta", when)
+        return N.TSlab(self.d4[b.ind_before].data_ptr(), self.d4[b.ind_after].data_ptr(), b.x_hi, b.x_new)
 
 
 class Pending:
@@ -251,7 +269,8 @@ class PGWEngine:
         for name in ("PS", "FIS", "FR_LAND", "FR_SEA_ICE", "T_SKIN", "T", "QV", "U", "V"):
             setattr(a, name, f[name].data_ptr())
         a.T_SO = f["T_SO"].data_ptr() if nsoil else 0
-        for name in ("ta", "hur", "ua", "va", "tas", "hurs", "ps_hist", "ts", "tos", "siconc"):
+        a.d4 = ds.slab4(era_step_dt)
+        for name in ("tas", "hurs", "ps_hist", "ts", "tos", "siconc"):
             setattr(a, name, ds.slab(name, era_step_dt))
         a.zg_ref = ds.slab("zg", era_step_dt, level=int(sel[0]))
         a.ts_clim = ds.ts_clim.data_ptr()
