@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpgw_b200.so")
+# PGW_B200_LIB selects another build of the same library (kernel A/B runs)
+LIB_PATH = os.environ.get("PGW_B200_LIB") or os.path.join(_HERE, "libpgw_b200.so")
 
 PGW_MAX_SOIL = 16
 PGW_MAX_ITER = 64

@@ -8,7 +8,10 @@
 namespace pgw {
 
 constexpr int kColumnThreads = 128;  // columns per CTA (= TMA box width)
-constexpr int kL2Ahead = 6;          // delta nodes pulled into L2 this many steps ahead of their use
+#ifndef PGW_NODE_L2_AHEAD
+#define PGW_NODE_L2_AHEAD 3
+#endif
+constexpr int kL2Ahead = PGW_NODE_L2_AHEAD;   // delta nodes pulled into L2 this many steps ahead of their use
 
 // Raw (before, after) pair of a 2-D delta; all pairs of a column are loaded up front so
 // that their DRAM latencies overlap, then blended.

@@ -32,7 +32,10 @@
 namespace pgw {
 
 constexpr int kTmaSlots = 4;         // ring of level pairs, 4 KB each
-constexpr int kTmaL2Ahead = 6;       // level pairs prefetched into L2 beyond the ones in the ring
+#ifndef PGW_TMA_L2_AHEAD
+#define PGW_TMA_L2_AHEAD 0
+#endif
+constexpr int kTmaL2Ahead = PGW_TMA_L2_AHEAD;   // level pairs prefetched into L2 beyond the ones in the ring
 constexpr int kTmaMaxLev = 160;      // capacity of the parameter-space table of the upper levels
 
 // tiled tensor maps [nlev, ncol] (box 2 x 128) of the four 3-D inputs and outputs, and (akm, bkm)
