@@ -41,6 +41,7 @@ extern "C" {
 #define PGW_ERR_EXTRAP_OFF          (1u << 2)  /* functions.py:564-566 */
 #define PGW_ERR_PS_HIST_RANGE       (1u << 4)  /* functions.py:360-361,363 */
 #define PGW_ERR_PREF_BELOW_SFC      (1u << 5)  /* functions.py:162-165 */
+#define PGW_ERR_NO_PREF             (1u << 6)  /* step_03_apply_to_era.py:245-251 */
 #define PGW_ERR_PS_BOUND            (1u << 7)  /* ps left the range the column
                                                   stash was sized for: rerun
                                                   with a larger ps_bound */
@@ -255,6 +256,36 @@ typedef struct pgw_timestep_result {
 
 int pgw_timestep_finalize(const pgw_timestep_args *a, pgw_timestep_result *result_dev,
                           void *stream);
+
+/* ------------------------------------------------------------------------
+ * The staged per-timestep path: pgw_for_era5() run stage by stage on float64
+ * device arrays with the operators above plus the small ones below.  It covers
+ * the settings the fused pass does not, i_reinterp = 1
+ * (step_03_apply_to_era.py:202-216, :330-343) and p_ref_inp = None (:219-251);
+ * host orchestration: pgw4era5_b200/staged.py.
+ *   pgw_surface_update        sea ice / skin / soil block, step_03:103-146
+ *                             (reads only the 2-D members of the args)
+ *   pgw_hybrid_pressure_f64   p[l,c] = a[l] + ps[c]*b[l], step_03:64-88,:196-199
+ *   pgw_axpy_f64              out = x + alpha*y (delta application :169-172,
+ *                             ps update :192-193)
+ *   pgw_determine_p_ref_f64   determine_p_ref per column, functions.py:583-598;
+ *                             opts in the order of the zg file; p_ref_last NULL
+ *                             in the first iteration; PGW_ERR_NO_PREF if none
+ *   pgw_select_plev_f64       field.sel(plev = p_ref[c]) per column, :292-295
+ *   pgw_ps_adjust_f64         phi_ref_error, adj_ps and atomicMax of |error|
+ *                             (float64 bits in *maxerr), step_03:286-308
+ * ---------------------------------------------------------------------- */
+int pgw_surface_update(const pgw_timestep_args *a, void *stream);
+int pgw_hybrid_pressure_f64(const double *ps, const double *a, const double *b, double *out, int nlev,
+                            long long ncol, void *stream);
+int pgw_axpy_f64(const double *x, const double *y, double alpha, double *out, long long n, void *stream);
+int pgw_determine_p_ref_f64(const double *p_min_era, const double *p_min_pgw, const double *opts, int nopt,
+                            const double *p_ref_last, double *out, long long n, uint32_t *err, void *stream);
+int pgw_select_plev_f64(const double *field, const double *plev, int K, const double *p_ref, double *out,
+                        long long n, void *stream);
+int pgw_ps_adjust_f64(const double *phi_pgw, const double *phi_era, const double *dphi_clim, const double *ps_pgw,
+                      const double *ta_low, double adj_factor, double *adj, uint64_t *maxerr, long long n,
+                      void *stream);
 
 /* ------------------------------------------------------------------------
  * step_02: bilinear regridding and annual-cycle smoothing.

@@ -534,9 +534,12 @@ def regrid_lat_lon(data, lat_gcm, lon_gcm, targ_lat, targ_lon):
 # ---------------------------------------------------------------------------
 def pgw_for_era5(era, deltas, era_step_dt, *, p_ref_inp=30000, adj_factor=0.95,
                  thresh_phi_ref_max_error=0.15, max_n_iter=20,
-                 ignore_top_pressure_error=False, n_iter_fixed=None):
+                 ignore_top_pressure_error=False, n_iter_fixed=None, i_reinterp=0):
     """
-    step_03_apply_to_era.py:44-381 with i_reinterp=0 and a scalar p_ref.
+    step_03_apply_to_era.py:44-381.  ``i_reinterp`` (settings.py:150) re-interpolates the ERA
+    state and the deltas onto the updated model levels every iteration (:202-216, :330-343);
+    ``p_ref_inp=None`` picks the reference pressure per column and iteration from the zg
+    pressure levels (:219-251, determine_p_ref).
 
     era:    dict of float arrays: ak,bk [L+1]; optionally akm,bkm [L];
             PS [1,ny,nx]; FIS [1,ny,nx]; T,QV,U,V [1,L,ny,nx]; FR_LAND,
@@ -584,17 +587,21 @@ def pgw_for_era5(era, deltas, era_step_dt, *, p_ref_inp=30000, adj_factor=0.95,
     out_deltas = {"ts": delta_ts_combined, "st": delta_soilt}
     vars_era = {"ta": T, "hur": RELHUM, "ua": U, "va": V}
     vars_pgw = {}
-    for var in ["ta", "hur", "ua", "va"]:
+    def delta_on(var, target_P):                              # load_delta_interp, functions.py:306-340
         d = load_delta(deltas[var], era_step_dt)
         if var in ("ta", "hur"):                             # functions.py:325-332
             d_sfc = load_delta(deltas[var + "s"], era_step_dt)
             ps_hist = load_delta(deltas["ps_hist"], era_step_dt)
         else:
             d_sfc = ps_hist = None
-        dv = vert_interp_delta(d, deltas[var]["plev"], pa_era, d_sfc, ps_hist,
-                               ignore_top_pressure_error)
-        out_deltas[var] = dv
-        vars_pgw[var] = vars_era[var] + dv
+        return vert_interp_delta(d, deltas[var]["plev"], target_P, d_sfc, ps_hist,
+                                 ignore_top_pressure_error)
+
+    if not i_reinterp:                                       # :155-173
+        for var in ["ta", "hur", "ua", "va"]:
+            dv = delta_on(var, pa_era)
+            out_deltas[var] = dv
+            vars_pgw[var] = vars_era[var] + dv
 
     # ---- iterative surface-pressure adjustment (:182-319)
     delta_ps = np.zeros_like(PS)
@@ -603,6 +610,7 @@ def pgw_for_era5(era, deltas, era_step_dt, *, p_ref_inp=30000, adj_factor=0.95,
     errs = []
     it = 1
     plev_zg = f64(deltas["zg"]["plev"])
+    p_ref_field = None
     ps_traj, hus_traj = [], []
     while (phi_ref_max_error > thresh_phi_ref_max_error if n_iter_fixed is None
            else it <= n_iter_fixed):
@@ -610,7 +618,26 @@ def pgw_for_era5(era, deltas, era_step_dt, *, p_ref_inp=30000, adj_factor=0.95,
         ps_pgw = PS + delta_ps
         pa_pgw = lev(akm) + ps_pgw[:, None] * lev(bkm)
         pa_hl_pgw = lev(ak) + ps_pgw[:, None] * lev(bk)
-        p_ref = p_ref_inp
+        if i_reinterp:                                       # :202-216
+            for var in ["ta", "hur"]:
+                v_era = interp_logp_4d(vars_era[var], pa_era, pa_pgw, extrapolate="constant")
+                out_deltas[var] = delta_on(var, pa_pgw)
+                vars_pgw[var] = v_era + out_deltas[var]
+        if p_ref_inp is None:                                # :219-251
+            p_min_era = pa_hl_era[:, -1] * 0.95
+            p_min_pgw = pa_hl_pgw[:, -1] * 0.95
+            p_new = np.full(PS.shape, np.nan)
+            for idx in np.ndindex(PS.shape):
+                r = determine_p_ref(p_min_era[idx], p_min_pgw[idx], plev_zg,
+                                    None if p_ref_field is None else p_ref_field[idx])
+                p_new[idx] = np.nan if r is None else r
+            p_ref_field = p_new
+            if np.any(np.isnan(p_ref_field)):
+                raise ValueError("No reference pressure level above the required local minimum "
+                                 "pressure level could not be found everywhere.")
+            p_ref = p_ref_field
+        else:
+            p_ref = p_ref_inp
         vars_pgw["hus"] = relative_to_specific_humidity(
             vars_pgw["hur"], pa_pgw, vars_pgw["ta"])
         phi_ref_pgw = integ_geopot(pa_hl_pgw, f64(era["FIS"]), vars_pgw["ta"],
@@ -618,10 +645,14 @@ def pgw_for_era5(era, deltas, era_step_dt, *, p_ref_inp=30000, adj_factor=0.95,
         phi_ref_era = integ_geopot(pa_hl_era, f64(era["FIS"]), T, QV, p_ref)
         delta_phi_ref = phi_ref_pgw - phi_ref_era
         dzg = load_delta(deltas["zg"], era_step_dt) * CON_G  # :292-295
-        sel = np.nonzero(plev_zg == p_ref)[0]
-        if len(sel) != 1:
-            raise KeyError("p_ref not found among zg pressure levels")
-        climate_delta_phi_ref = dzg[:, sel[0]]
+        if p_ref_inp is None:                                # .sel(plev=p_ref), pointwise
+            lev_idx = np.argmax(plev_zg[None, :, None, None] == p_ref[:, None], axis=1)
+            climate_delta_phi_ref = np.take_along_axis(dzg, lev_idx[:, None], axis=1)[:, 0]
+        else:
+            sel = np.nonzero(plev_zg == p_ref)[0]
+            if len(sel) != 1:
+                raise KeyError("p_ref not found among zg pressure levels")
+            climate_delta_phi_ref = dzg[:, sel[0]]
         phi_ref_error = delta_phi_ref - climate_delta_phi_ref
         adj_ps = - adj_factor * ps_pgw / (CON_RD * vars_pgw["ta"][:, -1]) * phi_ref_error
         with np.errstate(invalid="ignore"):
@@ -635,7 +666,13 @@ def pgw_for_era5(era, deltas, era_step_dt, *, p_ref_inp=30000, adj_factor=0.95,
         if n_iter_fixed is None and it > max_n_iter:
             raise ValueError("ERROR! Pressure adjustment did not converge")
     out_deltas["ps"] = ps_pgw - PS
+    if i_reinterp:                                           # :330-343
+        for var in ["ua", "va"]:
+            v_era = interp_logp_4d(vars_era[var], pa_era, pa_pgw, extrapolate="constant")
+            out_deltas[var] = delta_on(var, pa_pgw)
+            vars_pgw[var] = v_era + out_deltas[var]
     return dict(PS=ps_pgw, T=vars_pgw["ta"], QV=vars_pgw["hus"], U=vars_pgw["ua"],
                 V=vars_pgw["va"], T_SKIN=T_SKIN, T_SO=T_SO, FR_SEA_ICE=sic,
                 n_iter=it - 1, phi_max_errors=errs, deltas=out_deltas,
-                RELHUM_era=RELHUM, ps_traj=ps_traj, hus_traj=hus_traj)
+                RELHUM_era=RELHUM, ps_traj=ps_traj, hus_traj=hus_traj,
+                p_ref=p_ref if p_ref_inp is None else None)

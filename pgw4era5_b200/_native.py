@@ -23,6 +23,7 @@ ERR_TARG_NOT_ASCENDING = 1 << 1
 ERR_EXTRAP_OFF = 1 << 2
 ERR_PS_HIST_RANGE = 1 << 4
 ERR_PREF_BELOW_SFC = 1 << 5
+ERR_NO_PREF = 1 << 6
 ERR_PS_BOUND = 1 << 7
 
 EXTRAP_MODES = {"off": 0, "linear": 1, "constant": 2, "nan": 3}
@@ -91,6 +92,12 @@ def _load():
         "pgw_zonal_mean_f32": (i, [vp, vp, ll, i, i, vp]),
         "pgw_regrid_bilinear_f32": (i, [vp, vp, vp, ll, i, i, i, i, vp, vp, vp, vp, vp, vp, vp]),
         "pgw_smooth_harmonic_f32": (i, [vp, vp, i, ll, vp]),
+        "pgw_surface_update": (i, [C.POINTER(TimestepArgs), vp]),
+        "pgw_hybrid_pressure_f64": (i, [vp, vp, vp, vp, i, ll, vp]),
+        "pgw_axpy_f64": (i, [vp, vp, d, vp, ll, vp]),
+        "pgw_determine_p_ref_f64": (i, [vp, vp, vp, i, vp, vp, ll, vp, vp]),
+        "pgw_select_plev_f64": (i, [vp, vp, i, vp, vp, ll, vp]),
+        "pgw_ps_adjust_f64": (i, [vp, vp, vp, vp, vp, d, vp, vp, ll, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

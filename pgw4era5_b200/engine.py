@@ -220,10 +220,39 @@ class PGWEngine:
         T, QV, U, V [1,L,ny,nx] (the names of settings.var_name_map).  Returns a
         ``Pending``; nothing is synchronised here.
         """
-        if settings.i_reinterp:
-            raise NotImplementedError("i_reinterp = 1 is not on the CUDA path (SURVEY.md 8f, rank 2)")
-        if settings.p_ref_inp is None:
-            raise NotImplementedError("p_ref_inp = None is not on the CUDA path (SURVEY.md 8f, rank 2)")
+        if settings.i_reinterp or settings.p_ref_inp is None:
+            raise ValueError("i_reinterp = 1 / p_ref_inp = None run through the staged path: use apply()")
+        a, f, out, ws, k_spec, k_max = self._fill_args(era, era_step_dt, out, k_spec, slot)
+        status = ws["status"]
+        base = status.data_ptr()
+        result_ptr = base + 8 * N.PGW_MAX_ITER
+        status[8 * N.PGW_MAX_ITER + 24:].zero_()                          # clear the sticky error word
+        st = _stream()
+        if self.kernel_events is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        N.check(N.lib.pgw_timestep(C.byref(a), st), "pgw_timestep")
+        if self.kernel_events is not None:
+            e1.record()
+            self.kernel_events.append((e0, e1))
+        self.stats["launches"] += 4
+        if self.group is not None:
+            # latitude-band mode: the stopping rule is global over all bands
+            import torch.distributed as dist
+            maxerr = status[:8 * N.PGW_MAX_ITER].view(torch.float64)
+            dist.all_reduce(maxerr, op=dist.ReduceOp.MAX, group=self.group)
+        N.check(N.lib.pgw_timestep_finalize(C.byref(a), C.c_void_p(result_ptr), st), "pgw_timestep_finalize")
+        host = torch.empty(_STATUS_BYTES, dtype=torch.uint8, pin_memory=True)
+        host.copy_(status, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        ctx = dict(era=era, when=era_step_dt, ignore_top=ignore_top_pressure_error, k_spec=k_spec,
+                   k_max=k_max, keep=(f, a), file_name=file_name, slot=slot)
+        return Pending(self, a, out, host, ev, ctx)
+
+    def _fill_args(self, era, era_step_dt, out=None, k_spec=None, slot=0):
+        """Validate the ERA5 fields and fill a ``pgw_timestep_args`` for them.  Returns
+        (args, input tensors, outputs, workspace, k_spec, k_max)."""
         ds = self.deltas
         ny, nx = era["PS"].shape[-2:]
         ncol = ny * nx
@@ -254,9 +283,13 @@ class PGWEngine:
         status = ws["status"]
 
         zg = ds.vars["zg"]
-        sel = np.nonzero(zg["plev"] == float(settings.p_ref_inp))[0]      # .sel(plev=p_ref), step_03:294
-        if len(sel) != 1:
-            raise KeyError(float(settings.p_ref_inp))
+        if settings.p_ref_inp is None:                                    # staged path: level picked per column
+            sel, p_ref_scalar = [0], float(zg["plev"][0])
+        else:
+            p_ref_scalar = float(settings.p_ref_inp)
+            sel = np.nonzero(zg["plev"] == p_ref_scalar)[0]               # .sel(plev=p_ref), step_03:294
+            if len(sel) != 1:
+                raise KeyError(p_ref_scalar)
 
         a = N.TimestepArgs()
         a.ncol, a.nlev, a.nplev, a.nsoil = ncol, L, len(ds.plev), nsoil
@@ -276,7 +309,7 @@ class PGWEngine:
         a.ts_clim = ds.ts_clim.data_ptr()
         for i, v in enumerate(self.soil_decay):
             a.soil_decay[i] = float(v)
-        a.p_ref = float(settings.p_ref_inp)
+        a.p_ref = p_ref_scalar
         a.adj_factor = float(settings.adj_factor)
         a.thresh_phi_ref_max_error = float(settings.thresh_phi_ref_max_error)
         a.k_spec = k_spec
@@ -292,31 +325,7 @@ class PGWEngine:
         a.maxerr = base
         a.stats = base + 8 * N.PGW_MAX_ITER + 16
         a.err = base + 8 * N.PGW_MAX_ITER + 24
-        result_ptr = base + 8 * N.PGW_MAX_ITER
-
-        status[8 * N.PGW_MAX_ITER + 24:].zero_()                          # clear the sticky error word
-        st = _stream()
-        if self.kernel_events is not None:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-        N.check(N.lib.pgw_timestep(C.byref(a), st), "pgw_timestep")
-        if self.kernel_events is not None:
-            e1.record()
-            self.kernel_events.append((e0, e1))
-        self.stats["launches"] += 4
-        if self.group is not None:
-            # latitude-band mode: the stopping rule is global over all bands
-            import torch.distributed as dist
-            maxerr = status[:8 * N.PGW_MAX_ITER].view(torch.float64)
-            dist.all_reduce(maxerr, op=dist.ReduceOp.MAX, group=self.group)
-        N.check(N.lib.pgw_timestep_finalize(C.byref(a), C.c_void_p(result_ptr), st), "pgw_timestep_finalize")
-        host = torch.empty(_STATUS_BYTES, dtype=torch.uint8, pin_memory=True)
-        host.copy_(status, non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record()
-        ctx = dict(era=era, when=era_step_dt, ignore_top=ignore_top_pressure_error, k_spec=k_spec,
-                   k_max=k_max, keep=(f, a), file_name=file_name, slot=slot)
-        return Pending(self, a, out, host, ev, ctx)
+        return a, f, out, ws, k_spec, k_max
 
     # ------------------------------------------------------------------ completion
     def _complete(self, p):
@@ -373,5 +382,11 @@ class PGWEngine:
         return err, m[0], m[1]
 
     def apply(self, era, era_step_dt, **kw):
-        """Synchronous form of ``submit``: returns the output dict (device tensors)."""
+        """Synchronous form of ``submit``: returns the output dict (device tensors).  The settings
+        the fused pass does not cover (i_reinterp = 1, p_ref_inp = None) take the staged path."""
+        if settings.i_reinterp or settings.p_ref_inp is None:
+            from . import staged
+            kw.pop("k_spec", None)
+            kw.pop("slot", None)
+            return staged.apply_staged(self, era, era_step_dt, **kw)
         return self.submit(era, era_step_dt, **kw).result()

@@ -114,3 +114,24 @@ def test_oracle_raises_like_reference():
     bad["ps_hist"] = dict(deltas["ps_hist"], data=deltas["ps_hist"]["data"] * 0 + 50.0)
     with pytest.raises(ValueError):
         run_oracle(era, bad)
+
+
+def test_oracle_variants_i_reinterp_and_local_p_ref():
+    """step_03:202-251,:330-343 restated in the oracle: sanity of the two non-default settings."""
+    import numpy as np
+    from cases import make_case, run_oracle
+    era, deltas = make_case(5, 8, 3)
+    base = run_oracle(era, deltas)
+    same = run_oracle(era, deltas, i_reinterp=0, p_ref_inp=30000)
+    assert same["n_iter"] == base["n_iter"] and np.array_equal(same["PS"], base["PS"])
+    re = run_oracle(era, deltas, i_reinterp=1)
+    loc = run_oracle(era, deltas, p_ref_inp=None)
+    # the first iteration does not depend on i_reinterp (pa_pgw == pa_era): same first error
+    assert abs(re["phi_max_errors"][0] - base["phi_max_errors"][0]) < 1e-9
+    plev = np.asarray(deltas["zg"]["plev"], dtype=np.float64)
+    assert np.all(np.isin(loc["p_ref"], plev))
+    ps = np.asarray(era["PS"], dtype=np.float64)
+    assert np.all(loc["p_ref"] < 0.95 * np.minimum(ps, loc["PS"]) + 1e-9)
+    for r in (re, loc):
+        assert r["phi_max_errors"][-1] <= 0.15 < r["phi_max_errors"][-2]
+        assert np.all(np.isfinite(r["PS"])) and float(np.abs(r["PS"] - base["PS"]).max()) < 200.0

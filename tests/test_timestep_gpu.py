@@ -235,3 +235,35 @@ def test_odd_ncol_takes_generic_flavour():
     era, deltas = make_case(7, 31, 3)
     eng = _engine(era, deltas)
     assert _uses_tma(eng, era) == 0
+
+
+@pytest.mark.parametrize("i_reinterp,p_ref_inp", [(1, 30000), (0, None), (1, None)])
+def test_staged_path_variants(i_reinterp, p_ref_inp):
+    """i_reinterp = 1 and p_ref_inp = None run through the staged path
+    (pgw4era5_b200/staged.py) and match the oracle's restatement of step_03:202-251,:330-343."""
+    from pgw4era5_b200 import settings
+    era, deltas = make_case(12, 20, 4)
+    ref = run_oracle(era, deltas, i_reinterp=i_reinterp, p_ref_inp=p_ref_inp)
+    old = settings.i_reinterp, settings.p_ref_inp
+    settings.i_reinterp, settings.p_ref_inp = i_reinterp, p_ref_inp
+    try:
+        res, _ = _apply(era, deltas)
+    finally:
+        settings.i_reinterp, settings.p_ref_inp = old
+    np.testing.assert_allclose(res["phi_max_errors"], ref["phi_max_errors"], rtol=0, atol=1e-3)
+    _check(res, ref)
+    if p_ref_inp is None:
+        np.testing.assert_array_equal(res["p_ref"].cpu().numpy(), ref["p_ref"])
+
+
+def test_staged_path_equals_fused_for_default_settings():
+    """The staged path run with the default settings (forced) agrees with the fused kernel."""
+    from pgw4era5_b200 import staged
+    era, deltas = make_case(12, 20, 4)
+    eng = _engine(era, deltas)
+    res_f = eng.apply(_dev(era), ERA_DATE, ignore_top_pressure_error=True)
+    fused = {k: v.clone() for k, v in res_f.items() if isinstance(v, torch.Tensor)}
+    res_s = staged.apply_staged(eng, _dev(era), ERA_DATE, ignore_top_pressure_error=True)
+    assert res_s["n_iter"] == res_f["n_iter"]
+    for name in ("PS", "T", "QV", "U", "V", "T_SKIN", "T_SO", "FR_SEA_ICE"):
+        assert float((res_s[name] - fused[name]).abs().nan_to_num().max()) <= TOL[name], name
