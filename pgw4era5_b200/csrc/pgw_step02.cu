@@ -76,6 +76,89 @@ regrid_kernel(const float *__restrict__ src, float *__restrict__ dst, const floa
     }
 }
 
+// Row-wise variant for target rows that fit one CTA (nx_t / VEC <= blockDim, nx_s <= 2048), the
+// case of every ERA5 grid: a CTA walks over (field, target row) pairs.  Per row, (A) the two
+// bracketing source rows are blended in latitude ONCE per source column into shared memory
+// (functions.py:859), (B) every thread produces VEC adjacent target longitudes from that row with
+// the longitude brackets and weights it keeps in registers for the whole kernel (:892).  The blended
+// row is double buffered, so one barrier per row suffices.  Same expressions, hence bit-identical
+// to regrid_kernel, at about a quarter of its instructions per point: the 16x larger target field
+// makes this a store-bound kernel.
+template <int VEC>
+__global__ void __launch_bounds__(384)
+regrid_rows_kernel(const float *__restrict__ src, float *__restrict__ dst, const float *__restrict__ polemean,
+                   int nfield, int ny_s, int nx_s, int ny_t, int nx_t, const int *__restrict__ j0,
+                   const int *__restrict__ j1, const double *__restrict__ wy, const int *__restrict__ i0,
+                   const int *__restrict__ i1, const double *__restrict__ wx) {
+    extern __shared__ double2 s_row[];              // [2 buffers][nx_s] (row of jt0, row of jt1)
+    const int nxv = nx_t / VEC;
+    const int tid = threadIdx.x;
+    const bool owner = tid < nxv;
+    int ia[VEC], ib[VEC];
+    double w[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+        const int it = owner ? tid * VEC + v : 0;
+        ia[v] = i0[it]; ib[v] = i1[it]; w[v] = wx[it];
+    }
+    // work item = a PAIR of adjacent target rows (2 jp, 2 jp + 1) of one field.  The gathers of the
+    // next item are issued before the barrier of the current one (registers), so their L2 latency
+    // overlaps the longitude pass and the stores.
+    const int npair = (ny_t + 1) >> 1;
+    const int step_f = (int)(gridDim.x / (unsigned)npair), step_p = (int)(gridDim.x % (unsigned)npair);
+    int f = (int)(blockIdx.x / (unsigned)npair), jp = (int)(blockIdx.x % (unsigned)npair);
+    const int i_src = tid < nx_s ? tid : nx_s - 1;              // nx_s <= blockDim: one source column per thread
+    float g[4];                                                 // src values at (ja0, jb0, ja1, jb1) x i_src
+    double wj0 = 0.0, wj1 = 0.0;
+    auto gather = [&](int ff, int jpp) {
+        const int jt0 = 2 * jpp, jt1 = min(jt0 + 1, ny_t - 1);
+        const float *fld = src + (unsigned)ff * (unsigned)(ny_s * nx_s);
+        const float *pm = polemean + ff * 2;
+        const int jj[4] = {j0[jt0], j1[jt0], j0[jt1], j1[jt1]};
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            g[k] = jj[k] >= 0 ? __ldg(fld + (unsigned)(jj[k] * nx_s + i_src)) : __ldg(pm + (-1 - jj[k]));
+        wj0 = wy[jt0]; wj1 = wy[jt1];
+    };
+    if (f < nfield) gather(f, jp);
+    int buf = 0;
+    while (f < nfield) {
+        double2 *row = s_row + buf * nx_s;
+        {
+            const double a0 = (double)g[0], a1 = (double)g[1], c0 = (double)g[2], c1 = (double)g[3];
+            if (tid < nx_s) row[tid] = make_double2((a1 - a0) * wj0 + a0, (c1 - c0) * wj1 + c0);
+        }
+        const int fc = f, jt0 = 2 * jp;
+        const bool two = jt0 + 1 < ny_t;
+        f += step_f; jp += step_p;
+        if (jp >= npair) { jp -= npair; ++f; }
+        if (f < nfield) gather(f, jp);
+        __syncthreads();
+        if (owner) {
+            float r0[VEC], r1[VEC];
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                const double2 a = row[ia[v]], b = row[ib[v]];
+                r0[v] = (float)((b.x - a.x) * w[v] + a.x);
+                r1[v] = (float)((b.y - a.y) * w[v] + a.y);
+            }
+            float *o0 = dst + ((long long)fc * ny_t + jt0) * nx_t + tid * VEC;
+            float *o1 = o0 + nx_t;
+            if (VEC == 4) {
+                __stcs(reinterpret_cast<float4 *>(o0), make_float4(r0[0], r0[1], r0[2], r0[3]));
+                if (two) __stcs(reinterpret_cast<float4 *>(o1), make_float4(r1[0], r1[1], r1[2], r1[3]));
+            } else {
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) {
+                    __stcs(o0 + v, r0[v]);
+                    if (two) __stcs(o1 + v, r1[v]);
+                }
+            }
+        }
+        buf ^= 1;
+    }
+}
+
 // harmonic_ac_analysis (functions.py:678-740): mean + harmonics 1..3 of an
 // nt-long series per grid point.  One thread per grid point, lanes = adjacent
 // points; cos/sin tables for the three harmonics are staged in shared memory.
@@ -136,6 +219,18 @@ int pgw_regrid_bilinear_f32(const float *src, float *dst, const float *polemean,
     if (!src || !dst || !polemean || !j0 || !j1 || !wy || !i0 || !i1 || !wx) return PGW_E_INVALID;
     if (nfield <= 0 || ny_s < 1 || nx_s < 1 || ny_t < 1 || nx_t < 1) return PGW_E_INVALID;
     const bool vec = (nx_t % 4 == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+    if ((vec ? nx_t / 4 : nx_t) <= 384 && nx_s <= 384 && nfield * ny_s * (long long)nx_s < (1LL << 31)) {
+        const long long nitem = nfield * (long long)((ny_t + 1) / 2);
+        long long g = nitem < 148LL * 5 ? nitem : 148LL * 5;
+        const size_t smem = sizeof(double) * 4 * (size_t)nx_s;
+        if (vec)
+            regrid_rows_kernel<4><<<(unsigned)g, 384, smem, (cudaStream_t)stream>>>(
+                src, dst, polemean, (int)nfield, ny_s, nx_s, ny_t, nx_t, j0, j1, wy, i0, i1, wx);
+        else
+            regrid_rows_kernel<1><<<(unsigned)g, 384, smem, (cudaStream_t)stream>>>(
+                src, dst, polemean, (int)nfield, ny_s, nx_s, ny_t, nx_t, j0, j1, wy, i0, i1, wx);
+        return pgw_check_launch("regrid_rows_kernel");
+    }
     const long long total = nfield * ny_t * (long long)(vec ? nx_t / 4 : nx_t);
     long long g = (total + 255) / 256;
     const long long cap = 148LL * 32;
