@@ -31,7 +31,10 @@
 
 namespace pgw {
 
-constexpr int kTmaSlots = 4;         // ring of level pairs, 4 KB each
+#ifndef PGW_TMA_SLOTS
+#define PGW_TMA_SLOTS 4
+#endif
+constexpr int kTmaSlots = PGW_TMA_SLOTS;   // ring of level pairs, 4 KB each
 #ifndef PGW_TMA_L2_AHEAD
 #define PGW_TMA_L2_AHEAD 0
 #endif
@@ -54,7 +57,6 @@ __global__ void __launch_bounds__(kColumnThreads + 32, 3)
 pgw_column_tma_kernel(const __grid_constant__ pgw_timestep_args a, const __grid_constant__ TmaParams tp,
                       const int lst, const int np) {
     constexpr int NT = kColumnThreads;
-    constexpr int SM = kTmaSlots - 1;
     extern __shared__ __align__(1024) unsigned char smem[];
     const int L = a.nlev, K = a.nplev;
     // ---- shared memory: pair ring | stash | (ak,bk)[np+1] | (akm,bkm)[np] | plev tables | barriers
@@ -100,7 +102,7 @@ pgw_column_tma_kernel(const __grid_constant__ pgw_timestep_args a, const __grid_
         // so the last pair of an odd column is levels (1, 0): level 1 is simply done twice.
         auto pair_row = [&](int j) { const int r = L - 2 - 2 * j; return r < 0 ? 0 : r; };
         auto load_pair_slot = [&](int j) {
-            const int s = j & SM;
+            const int s = j % kTmaSlots;
             float *dst = ring + s * 8 * NT;
             mbar_arrive_expect_tx(bar_full + s, 4u * 2u * NT * sizeof(float));
 #pragma unroll
@@ -116,7 +118,7 @@ pgw_column_tma_kernel(const __grid_constant__ pgw_timestep_args a, const __grid_
         for (int j = kTmaSlots; j < kTmaSlots + kTmaL2Ahead; ++j) l2_pair(j);
 #pragma unroll 1
         for (int j = 0; j < npairs; ++j) {
-            const int s = j & SM;
+            const int s = j % kTmaSlots;
             const float *src = ring + s * 8 * NT;
             mbar_wait_backoff(bar_done + s, (j / kTmaSlots) & 1);
             const int row = pair_row(j);
@@ -254,7 +256,10 @@ pgw_column_tma_kernel(const __grid_constant__ pgw_timestep_args a, const __grid_
     }
 
     struct Dlt { float ta, hur, ua, va; };
-    auto walk = [&](float p) {
+    // element offset of node w_lo - 2 (the next one to fetch); one node down = +-ncol in the file
+    const int32_t off_step = desc ? (int32_t)n : -(int32_t)n;
+    uint32_t off_m = node_off(w_lo >= 2 ? w_lo - 2 : 0);
+    auto step_to = [&](float p) {
         while (w_p_lo > p) {
             const F4 hi = x_lo;
             --w_lo;
@@ -265,13 +270,20 @@ pgw_column_tma_kernel(const __grid_constant__ pgw_timestep_args a, const __grid_
                 n0 = m0; n1 = m1;
                 // the new loads are ordered behind the reads of the registers they replace
                 const int zero = reg_fence(n1.x, n1.y, n1.z, n1.w);
-                if (w_lo >= 2) { const uint32_t off = node_off(w_lo - 2 + zero); m0 = ldg4(d4lo + off); m1 = ldg4(d4hi + off); }
-                if (w_lo >= kL2Ahead) l2_node(w_lo - kL2Ahead);
+                off_m += off_step;
+                if (w_lo >= 2) { m0 = ldg4(d4lo + off_m + zero); m1 = ldg4(d4hi + off_m + zero); }
+                if (w_lo >= kL2Ahead) {
+                    const uint32_t off = off_m + (uint32_t)((kL2Ahead - 2) * off_step);
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(d4lo + off));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(d4hi + off));
+                }
             } else {
                 // above node 0: constant extrapolation with node 0's values; p_lo = 0 ends the walk
                 x_d = F4{0.f, 0.f, 0.f, 0.f}; w_inv_w = 0.0f; w_p_lo = 0.0f; w_inv_p_lo = 1.0f;
             }
         }
+    };
+    auto interp = [&](float p) {
         const float t = fast_lg2(p * w_inv_p_lo) * w_inv_w;
         // t == 0: exact node hit or constant extrapolation -> the node value itself (NaN-safe)
         const bool ex = (t == 0.0f);
@@ -282,6 +294,7 @@ pgw_column_tma_kernel(const __grid_constant__ pgw_timestep_args a, const __grid_
         d.va = ex ? x_lo.w : fmaf(t, x_d.w, x_lo.w);
         return d;
     };
+    auto walk = [&](float p) { step_to(p); return interp(p); };
     auto sfc_override = [&](float p, Dlt &d) {
         if (bot_on) {
             if (p > b_p1) {
@@ -413,8 +426,8 @@ pgw_column_tma_kernel(const __grid_constant__ pgw_timestep_args a, const __grid_
         const int l = max(L - 1 - 2 * j, 1);          // last pair of an odd column: levels (1, 0) again
         float2 mm0, mm1;
         if (parked) { mm0 = s_m[l]; mm1 = s_m[l - 1]; } else { mm0 = tp.m[l]; mm1 = tp.m[l - 1]; }
-        float *const sl = ring + (j & SM) * 8 * NT + tid;
-        mbar_wait(bar_full + (j & SM), (j / kTmaSlots) & 1);
+        float *const sl = ring + (j % kTmaSlots) * 8 * NT + tid;
+        mbar_wait(bar_full + (j % kTmaSlots), (j / kTmaSlots) & 1);
         const float t0 = sl[NT], q0 = sl[3 * NT], u0 = sl[5 * NT], v0 = sl[7 * NT];    // row 1: level l
         const float t1 = sl[0], q1 = sl[2 * NT], u1 = sl[4 * NT], v1 = sl[6 * NT];     // row 0: level l-1
         const float p0 = fmaf(ps_f, mm0.y, mm0.x), p1 = fmaf(ps_f, mm1.y, mm1.x);
@@ -429,7 +442,7 @@ pgw_column_tma_kernel(const __grid_constant__ pgw_timestep_args a, const __grid_
         sl[0] = tp1; sl[4 * NT] = u1 + d1.ua; sl[6 * NT] = v1 + d1.va;
         if (parked) {
             fence_proxy_async();
-            mbar_arrive(bar_done + (j & SM));
+            mbar_arrive(bar_done + (j % kTmaSlots));
             pTe[0] = make_float2(tp0, e0);
             pTe[-NT] = make_float2(tp1, e1);
             pTe -= 2 * NT;
@@ -440,7 +453,7 @@ pgw_column_tma_kernel(const __grid_constant__ pgw_timestep_args a, const __grid_
             sl[3 * NT] = qv_from_e(e0, psn_f, mm0);       // functions.py:66-72 with the adjusted ps
             sl[2 * NT] = qv_from_e(e1, psn_f, mm1);
             fence_proxy_async();
-            mbar_arrive(bar_done + (j & SM));
+            mbar_arrive(bar_done + (j % kTmaSlots));
         }
     }
 
