@@ -85,4 +85,6 @@ class HostPipeline:
         return done
 
     def drain(self):
-        return [self._finish(s) for s in self.slots]
+        """Finish everything in flight; results in submission order (None for idle slots)."""
+        order = [(self.count + k) % self.nslots for k in range(self.nslots)]
+        return [self._finish(self.slots[i]) for i in order]

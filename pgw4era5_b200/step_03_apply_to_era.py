@@ -115,6 +115,117 @@ def pgw_for_era5(inp_era_file_path, out_era_file_path, delta_input_dir, era_step
     return res["n_iter"]
 
 
+_ERA_NAMES = lambda vmap: dict(PS=vmap['ps'], FIS=vmap['zgs'], FR_LAND=vmap['sftlf'], FR_SEA_ICE=vmap['sic'],
+                               T_SKIN=vmap['ts'], T_SO=vmap['st'], T=vmap['ta'], QV=vmap['hus'], U=vmap['ua'],
+                               V=vmap['va'])
+
+
+def pgw_for_era5_files(steps, delta_input_dir, ignore_top_pressure_error, debug_mode=None):
+    """
+    The production mode of ``pgw_for_era5`` for a LIST of files on one GPU, as a three-stage
+    pipeline: a reader thread decodes file i+1 into pinned host buffers and
+    a writer thread stores file i-1 while the GPU works on file i (``hostpipe.HostPipeline``:
+    H2D, fused pass and D2H of consecutive files overlap on two CUDA streams).  Results are
+    identical to calling ``pgw_for_era5`` file by file.  ``steps``: dicts with inp_era_file_path,
+    out_era_file_path, era_step_dt.  Returns the iteration counts.
+    """
+    import queue
+    import threading
+    from .hostpipe import HostPipeline, IN_FIELDS
+    if not steps:
+        return []
+    if debug_mode is not None or settings.i_reinterp or settings.p_ref_inp is None:
+        return [pgw_for_era5(delta_input_dir=delta_input_dir,
+                             ignore_top_pressure_error=ignore_top_pressure_error, debug_mode=debug_mode, **st)
+                for st in steps]
+    vmap = settings.var_name_map
+    names = _ERA_NAMES(vmap)
+    first = ncio.open_dataset(steps[0]["inp_era_file_path"], decode_cf=False)
+    eng = get_engine(delta_input_dir, first)
+    ny, nx = first[names["PS"]].data.shape[-2:]
+    pipe = HostPipeline(eng, ny, nx)
+    n_in_buf, n_out_buf = 3, 4
+    free_in, free_out = queue.Queue(), queue.Queue()
+    for _ in range(n_in_buf):
+        free_in.put(pipe.alloc_host_inputs())
+    for _ in range(n_out_buf):
+        free_out.put(pipe.alloc_host_outputs())
+    loaded, to_write = queue.Queue(maxsize=n_in_buf), queue.Queue()
+    failure = []
+
+    def reader():
+        try:
+            for k, st in enumerate(steps):
+                if settings.i_debug >= 0:
+                    print('Start working on input file {}'.format(st["inp_era_file_path"]))
+                era_file = first if k == 0 else ncio.open_dataset(st["inp_era_file_path"], decode_cf=False)
+                h = free_in.get()
+                for key in IN_FIELDS:
+                    h[key].numpy()[...] = np.asarray(era_file[names[key]].data, dtype=np.float32).reshape(h[key].shape)
+                loaded.put((st, era_file, h))
+        except BaseException as e:          # surfaced by the main thread
+            failure.append(e)
+        finally:
+            loaded.put(None)
+
+    def writer():
+        try:
+            while True:
+                item = to_write.get()
+                if item is None:
+                    return
+                st, era_file, host = item
+                for key in ("PS", "T", "QV", "U", "V", "T_SKIN", "T_SO", "FR_SEA_ICE"):
+                    ref = era_file[names[key]]
+                    era_file[names[key]] = ncio.Variable(
+                        ref.dims, host[key].numpy().reshape(ref.data.shape).astype(ref.data.dtype), ref.attrs)
+                if vmap['hur'] in era_file:
+                    del era_file[vmap['hur']]
+                era_file.to_netcdf(st["out_era_file_path"], mode='w')
+                era_file.close()
+                free_out.put(host)
+                if settings.i_debug >= 1:
+                    print('Done. Saved to file {}.'.format(st["out_era_file_path"]))
+        except BaseException as e:
+            failure.append(e)
+
+    tr, tw = threading.Thread(target=reader, daemon=True), threading.Thread(target=writer, daemon=True)
+    tr.start(); tw.start()
+    in_flight, n_iters = [], []          # FIFO of (step, era_file, host_in, host_out) per pipeline slot use
+
+    def retire(done):
+        st, era_file, h_in, h_out = in_flight.pop(0)
+        free_in.put(h_in)
+        n_iters.append(done["n_iter"])
+        to_write.put((st, era_file, h_out))
+
+    try:
+        while True:
+            item = loaded.get()
+            if item is None:
+                break
+            st, era_file, h_in = item
+            h_out = free_out.get()
+            done = pipe.run(h_in, st["era_step_dt"], h_out, ignore_top_pressure_error=ignore_top_pressure_error,
+                            file_name=st["inp_era_file_path"])
+            in_flight.append((st, era_file, h_in, h_out))
+            if done is not None:
+                retire(done)
+        for done in pipe.drain():
+            if done is not None:
+                retire(done)
+    finally:
+        to_write.put(None)
+        tw.join()
+    if failure:
+        raise failure[0]
+    return n_iters
+
+
+def _run_file_group(steps, **fargs):
+    return pgw_for_era5_files(steps, **fargs)
+
+
 def debug_interpolate_time(inp_era_file_path, out_era_file_path, delta_input_dir, era_step_dt,
                            ignore_top_pressure_error, debug_mode=None):
     """step_03_apply_to_era.py:387-414: write the deltas interpolated in time only."""
@@ -195,7 +306,17 @@ def main(argv=None):
         step_args.append(dict(inp_era_file_path=os.path.join(args.input_dir, name),
                               out_era_file_path=os.path.join(args.output_dir, name),
                               era_step_dt=era_step_dt))
-    if (args.debug_mode is None) or (args.debug_mode == 'interpolate_full'):
+    if args.debug_mode is None:
+        # production mode: every worker (GPU) gets its share of the files and pipelines reading,
+        # the CUDA pass and writing (the reference hands single files to its pool, :601-638)
+        groups = [dict(steps=step_args[w::IMP.njobs]) for w in range(IMP.njobs)]
+        IMP.run(_run_file_group, fargs, groups)
+        out = [None] * len(step_args)
+        for w, res in enumerate(IMP.output):
+            out[w::IMP.njobs] = res
+        IMP.output = out
+        return IMP.output
+    if args.debug_mode == 'interpolate_full':
         run_function = pgw_for_era5
     else:
         run_function = debug_interpolate_time
