@@ -148,3 +148,54 @@ def test_step_03_cli_pipelines_several_files(tmp_path):
         # files take the rewrite path (k_spec > N), which recovers e from the fp32 QV: a few ulps
         np.testing.assert_allclose(a["QV"].data, b["QV"].data, rtol=0, atol=5e-9, err_msg=name)
         assert "RELHUM" not in a
+
+
+def test_step_01_cfday_interp_to_plev(tmp_path):
+    """model levels -> pressure levels (CFday_interp_to_plev.py:92-159)."""
+    from oracle import pgw_oracle as O
+    from pgw4era5_b200.step_01_extract_deltas import CFday_interp_to_plev as C1
+    rng = np.random.default_rng(71)
+    nt, nl, ny, nx = 3, 12, 5, 7
+    b = np.linspace(1.0, 0.0, nl)                        # file order: surface first (descending pressure)
+    ap = np.linspace(0.0, 3000.0, nl)
+    ps = 1e5 + 2000 * rng.normal(size=(nt, ny, nx))
+    ta = (250 + 10 * rng.normal(size=(nt, nl, ny, nx))).astype(np.float32)
+    chunk = "20700101-20741231"
+    name = "ta_CFday_MPI-ESM1-2-HR_ssp585_r1i1p1f1_gn_%s.nc" % chunk
+    inp = tmp_path / "sub"; inp.mkdir()
+    ds = ncio.Dataset()
+    ds["time"] = ncio.Variable(("time",), np.arange(nt, dtype=np.float64), {"units": "days since 1850-01-01"})
+    ds["lev"] = ncio.Variable(("lev",), np.arange(nl, dtype=np.float64))
+    ds["lat"] = ncio.Variable(("lat",), np.linspace(-10, 10, ny)); ds["lon"] = ncio.Variable(("lon",), np.arange(nx) * 1.0)
+    ds["ap"] = ncio.Variable(("lev",), ap); ds["b"] = ncio.Variable(("lev",), b)
+    ds["ps"] = ncio.Variable(("time", "lat", "lon"), ps)
+    ds["ta"] = ncio.Variable(("time", "lev", "lat", "lon"), ta)
+    ds.to_netcdf(str(inp / name))
+    targ = np.array([101000., 90000., 70000., 50000., 20000., 5000., 1000.])
+    np.savetxt(str(tmp_path / "targ.dat"), targ)
+    C1.main(["ta", "ssp585", "--inp_dir", str(inp), "--out_base_dir", str(tmp_path / "out"),
+             "--target_p_file", str(tmp_path / "targ.dat"), "--times", chunk])
+    res = ncio.open_dataset(str(tmp_path / "out" / "MPI-ESM1-2-HR" / name))
+    np.testing.assert_array_equal(res["plev"].data, np.sort(targ)[::-1])
+    src_p = (ap[::-1][None, :, None, None] + b[::-1][None, :, None, None] * ps[:, None])
+    tp = np.broadcast_to(np.sort(targ)[None, :, None, None], (nt, len(targ), ny, nx))
+    ref = O.interp_logp_4d(ta[:, ::-1].astype(np.float64), src_p, tp, extrapolate="constant")[:, ::-1]
+    np.testing.assert_allclose(res["ta"].data, ref, rtol=0, atol=2e-5)
+    assert res["ta"].dims == ("time", "plev", "lat", "lon")
+
+
+def test_extpar_adapt(tmp_path):
+    """postproc_cosmo/extpar_adapt.py:13-35: T_CL += annual mean of the ts delta."""
+    from pgw4era5_b200.postproc_cosmo import extpar_adapt as E
+    era, deltas = make_case(6, 9, 81)
+    dd = tmp_path / "deltas"; dd.mkdir()
+    _write_deltas(str(dd), deltas, era["lat"], era["lon"])
+    t_cl = (280 + np.arange(54, dtype=np.float32)).reshape(6, 9)
+    ext = ncio.Dataset()
+    ext["rlat"] = ncio.Variable(("rlat",), era["lat"]); ext["rlon"] = ncio.Variable(("rlon",), era["lon"])
+    ext["T_CL"] = ncio.Variable(("rlat", "rlon"), t_cl.copy())
+    ext.to_netcdf(str(tmp_path / "extpar.nc"))
+    E.main([str(tmp_path / "extpar.nc"), "-d", str(dd)])
+    got = ncio.open_dataset(str(tmp_path / "extpar.nc"))["T_CL"].data
+    ts = np.asarray(S.to_numpy(deltas)["ts"]["data"], dtype=np.float64)
+    np.testing.assert_allclose(got, t_cl + ts.mean(axis=0), rtol=0, atol=1e-4)
