@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PGW_B200_ABI_VERSION 3
+#define PGW_B200_ABI_VERSION 4
 
 /* host-side return codes */
 #define PGW_OK               0
@@ -51,6 +51,10 @@ extern "C" {
 #define PGW_EXTRAP_LINEAR    1
 #define PGW_EXTRAP_CONSTANT  2
 #define PGW_EXTRAP_NAN       3
+
+/* pgw_timestep_args.flags */
+#define PGW_FLAG_DIRECT  1   /* take the cp.async flavour of the column kernel, which integrates every parked
+                                level in every iteration (the TMA flavour uses a polynomial in dps) */
 
 #define PGW_MAX_SOIL   16
 #define PGW_MAX_ITER   64
@@ -197,6 +201,8 @@ typedef struct pgw_timestep_args {
     int nsoil;              /* soil levels (<= PGW_MAX_SOIL)                   */
     int plev_descending;    /* 1: 3-D delta slabs are stored bottom-up
                                (pressure descending, CMIP6 order)              */
+    int flags;              /* PGW_FLAG_*                                      */
+    int reserved0;
     /* level tables, DEVICE float64 */
     const double *ak, *bk;      /* [nlev+1] */
     const double *akm, *bkm;    /* [nlev]   */

@@ -25,6 +25,7 @@ ERR_PS_HIST_RANGE = 1 << 4
 ERR_PREF_BELOW_SFC = 1 << 5
 ERR_NO_PREF = 1 << 6
 ERR_PS_BOUND = 1 << 7
+FLAG_DIRECT = 1
 
 EXTRAP_MODES = {"off": 0, "linear": 1, "constant": 2, "nan": 3}
 
@@ -38,7 +39,7 @@ class TSlab(C.Structure):
 class TimestepArgs(C.Structure):
     _fields_ = (
         [("ncol", C.c_longlong), ("nlev", C.c_int), ("nplev", C.c_int), ("nsoil", C.c_int),
-         ("plev_descending", C.c_int)]
+         ("plev_descending", C.c_int), ("flags", C.c_int), ("reserved0", C.c_int)]
         + [(n, c_fp) for n in ("ak", "bk", "akm", "bkm", "plev", "ak_host", "bk_host", "akm_host", "bkm_host")]
         + [(n, c_fp) for n in ("PS", "FIS", "FR_LAND", "FR_SEA_ICE", "T_SKIN", "T_SO", "T", "QV", "U", "V")]
         + [(n, TSlab) for n in ("d4", "tas", "hurs", "ps_hist", "ts", "tos", "siconc", "zg_ref")]

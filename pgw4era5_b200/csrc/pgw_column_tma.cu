@@ -39,6 +39,7 @@ constexpr int kTmaSlots = PGW_TMA_SLOTS;   // ring of level pairs, 4 KB each
 #define PGW_TMA_L2_AHEAD 0
 #endif
 constexpr int kTmaL2Ahead = PGW_TMA_L2_AHEAD;   // level pairs prefetched into L2 beyond the ones in the ring
+constexpr double kTaylorMaxRel = 0.012;    // |ps_pgw - ps_era| / ps_era up to which the polynomial of the fixed point is used
 constexpr int kTmaMaxLev = 160;      // capacity of the parameter-space table of the upper levels
 
 // tiled tensor maps [nlev, ncol] (box 2 x 128) of the four 3-D inputs and outputs, and (akm, bkm)
@@ -317,27 +318,62 @@ pgw_column_tma_kernel(const __grid_constant__ pgw_timestep_args a, const __grid_
     if (!era_open) errbits |= PGW_ERR_PREF_BELOW_SFC;
     float psn_f = ps_f;                             // ps used for QV; replaced after the iteration
 
-    // T_pgw is parked as fp32.  Its rounding residual r_l (|r_l| <= 1.5e-5 K) enters the
-    // geopotential as Rd * sum_l r_l dlnp_l; that sum is taken once with the ERA pressures
-    // (its change over the iteration is < 1e-8 m2/s2) and added to every iteration's sum.
-    double acc_res = 0.0, acc_pgw0 = 0.0, t_low_d = 0.0;
-    // ERA geopotential of one layer (functions.py:128-189), sequential in the column.  The first
-    // iteration of the fixed point (dps = 0) integrates the PGW state over the same pressures, so
-    // its sum is taken here as well and the iteration proper starts at k = 1.
-    auto era_layer = [&](int l, float p, float t, float q, float dta, float t_pgw, float e_pgw) {
+    // ---------------- the geopotential sums of the parked levels ----------------
+    // The fixed point needs phi(p_ref) of the PGW state for ps = PS + x, x = dps_k.  (T, e) of the parked
+    // levels are kept in shared memory, but instead of re-integrating all of them in every iteration, the
+    // sum over the layers that lie safely below p_ref is expanded ONCE, during the sweep, as a polynomial
+    // in x:
+    //   ln(P_h + b_h x) = ln P_h + u x - (u x)^2/2 + (u x)^3/3 - (u x)^4/4,  u = b_h / P_h <= 1/PS,
+    //   Tv_l(x) = T_l + (T c e/Q)(1 - w x + w^2 x^2 - w^3 x^3),  Q = p_l - 0.378 e,  w = bm_l / Q,
+    // dry part in float64 to x^4, humidity part (1 % of the sum) in float32 to x^3: for |x| <= 0.012 PS the
+    // truncation error is below 2e-5 m2/s2 (the fp32 storage of e costs as much).  Only the three layers
+    // around p_ref (whose membership changes with x) are integrated directly in every iteration.  A warp
+    // in which some column leaves that range in iteration k (the first step of the iteration can overshoot
+    // by several thousand Pa over high terrain) integrates all its parked levels for that k, as before.
+    // T_pgw enters as fp32; its rounding residual r_l (|r_l| <= 1.5e-5 K) enters the geopotential as
+    // Rd * sum_l r_l dlnp_l, taken once with the ERA pressures (change over the iteration < 1e-8 m2/s2).
+    double acc_res = 0.0, acc_T0 = 0.0, acc_part0 = 0.0, t_low_d = 0.0;
+    double S1 = 0.0, S2 = 0.0, S3 = 0.0, S4 = 0.0;            // sum_l T_l (ub^k - ut^k)
+    float H1 = 0.0f, H2 = 0.0f, H3 = 0.0f;                    // humidity part, coefficients of x, x^2, x^3
+    int lstar = -1;                                           // the layer that contains p_ref for x = 0
+    auto rcp64 = [](double v) { double r = rcp64_approx(v); return fma(r, fma(-v, r, 1.0), r); };
+    // add sgn * (contribution of the fully-below layer l) to the polynomial
+    auto taylor_add = [&](int l, double Pb, double Pt, double tpd, float hq, float w, float dl, double sgn) {
+        const double ub = s_hl[l + 1].y * rcp64(Pb), ut = s_hl[l].y * rcp64(Pt);
+        const double d1 = ub - ut, sm = ub + ut, m2 = ub * ut;
+        const double q2 = fma(sm, sm, -2.0 * m2);            // ub^2 + ut^2
+        const double d2 = d1 * sm, d3 = d1 * (q2 + m2), d4 = d2 * q2;
+        const double ts = sgn * tpd;
+        S1 = fma(ts, d1, S1); S2 = fma(ts, d2, S2); S3 = fma(ts, d3, S3); S4 = fma(ts, d4, S4);
+        const float D1 = (float)d1, D2 = -0.5f * (float)d2, D3 = (1.0f / 3.0f) * (float)d3;
+        const float hs = (float)sgn * hq, w2 = w * w;
+        H1 = fmaf(hs, fmaf(-w, dl, D1), H1);
+        H2 = fmaf(hs, fmaf(w2, dl, fmaf(-w, D1, D2)), H2);
+        H3 = fmaf(hs, fmaf(-w2 * w, dl, fmaf(w2, D1, fmaf(-w, D2, D3))), H3);
+    };
+    // One parked level, bottom-up: the ERA geopotential (functions.py:128-189), iteration 0 of the
+    // PGW state (same pressures) and the polynomial of the later iterations.
+    auto era_layer = [&](int l, float p, float bm, float t, float q, float dta, float t_pgw, float e_pgw) {
         if (era_open) {
             const double2 hl = s_hl[l];
-            double pt = fma(PSd, hl.y, hl.x);
-            if (pt < pref) { pt = pref; era_open = false; }     // layer that contains p_ref (:174-179)
+            const double Pt = fma(PSd, hl.y, hl.x);
+            double pt = Pt;
+            if (pt < pref) { pt = pref; era_open = false; lstar = l; }   // layer that contains p_ref (:174-179)
             const double td = (double)t, tpd = (double)t_pgw;
             const double tv = fma(td, 0.61 * (double)q, td);
             const float g = fast_rcp(fmaf(-0.378f, e_pgw, p));
-            const double tvp = fma(tpd, (double)((0.61f * 0.622f) * e_pgw * g), tpd);
+            const float hq_t = (0.61f * 0.622f) * e_pgw * g;         // (Tv - T) / T of the PGW state
+            const double tvp = fma(tpd, (double)hq_t, tpd);
             const double dl = ln_ratio<FAST>(pb_era, pt, lk);
             acc_era = fma(tv, dl, acc_era);
-            acc_pgw0 = fma(tvp, dl, acc_pgw0);
             acc_res = fma((td + (double)dta) - tpd, dl, acc_res);
-            pb_era = pt;
+            if (era_open) {
+                acc_T0 = fma(tvp, dl, acc_T0);
+                taylor_add(l, pb_era, Pt, tpd, t_pgw * hq_t, bm * g, (float)dl, 1.0);
+            } else {
+                acc_part0 = tvp * dl;
+            }
+            pb_era = Pt;
         }
     };
 
@@ -350,8 +386,30 @@ pgw_column_tma_kernel(const __grid_constant__ pgw_timestep_args a, const __grid_
         const double gdzg = blend_f64(a.zg_ref, r_zg) * kG;              // step_03:292-295
         const float2 *const bTe = st_Te + (size_t)(L - 1 - lst) * NT + tid;  // lowest level of the stash
         const double t_low = t_low_d;                                 // ta_pgw on the lowest level
+        const bool no_star = lstar < 0;                               // p_ref not reached among the parked levels
+        if (no_star) lstar = lst;
+        const double acc_k0 = acc_T0 + acc_part0;                     // iteration 0: x = 0, all layers
+        // the layer right below l* joins the directly integrated ones: take it out of the polynomial
+        const int ld_hi = min(lstar + 1, L - 1), ld_lo = max(lstar - 1, lst);
+        if (lstar + 1 <= L - 1) {
+            const int l = lstar + 1;
+            const double2 ht = s_hl[l], hb = s_hl[l + 1];
+            const float2 m = s_m[l];
+            const float2 te = bTe[-(L - 1 - l) * NT];
+            const double Pt = fma(PSd, ht.y, ht.x), Pb = fma(PSd, hb.y, hb.x);
+            const float g = fast_rcp(fmaf(-0.378f, te.y, fmaf(ps_f, m.y, m.x)));
+            const float hq_t = (0.61f * 0.622f) * te.y * g;
+            const double tpd = (double)te.x;
+            const double dl = ln_ratio<FAST>(Pb, Pt, lk);
+            acc_T0 = fma(-fma(tpd, (double)hq_t, tpd), dl, acc_T0);
+            taylor_add(l, Pb, Pt, tpd, te.x * hq_t, m.y * g, (float)dl, -1.0);
+        }
+        const double c1 = S1 + (double)H1, c2 = fma(-0.5, S2, (double)H2), c3 = fma(1.0 / 3.0, S3, (double)H3),
+                     c4 = -0.25 * S4;
+        const double2 h_hi = s_hl[ld_hi + 1];
+        const double x_max = kTaylorMaxRel * PSd;
         double dps = 0.0, adj = 0.0, psn = PSd;
-        int ltop = lst + 1;                 // first layer (from the top) lying entirely below p_ref
+        int ltop = lst + 1;                 // direct integration: first layer (from the top) entirely below p_ref
         float *traj = a.dps_traj + c;
         for (int k = 0; k < a.k_spec; ++k, traj += n) {
             dps += adj;
@@ -361,38 +419,48 @@ pgw_column_tma_kernel(const __grid_constant__ pgw_timestep_args a, const __grid_
             if (psn > a.ps_bound) errbits |= PGW_ERR_PS_BOUND;
             double pb = fma(psn, hl_sfc.y, hl_sfc.x);
             if (pb < pref) errbits |= PGW_ERR_PREF_BELOW_SFC;
+            // Tv = T (1 + 0.61 hus), hus = 0.622 e / (p - 0.378 e)   (functions.py:66-72, :144)
+            auto layer = [&](int l, const float2 te, double pt_or_ref, double acc_in) {
+                const float2 m = s_m[l];
+                const double Td = (double)te.x;
+                const float g = fast_rcp(fmaf(-0.378f, te.y, fmaf(psn_f, m.y, m.x)));
+                const double tv = fma(Td, (double)((0.61f * 0.622f) * te.y * g), Td);
+                return fma(tv, ln_ratio<FAST>(pb, pt_or_ref, lk), acc_in);
+            };
             double acc = acc_res;
+            // polynomial usable by every column of the warp for this x?
+            const double p_edge = fma(psn, h_hi.y, h_hi.x);       // bottom of the directly integrated layers
+            const bool poly_ok = !(no_star || !(fabs(dps) <= x_max) || p_edge < pref ||
+                                   fma(psn, s_hl[ld_lo].y, s_hl[ld_lo].x) >= pref);
             if (k == 0) {
-                acc += acc_pgw0;            // psn == PS: summed in phase 1 together with the ERA state
+                acc += acc_k0;              // psn == PS: summed in phase 1 together with the ERA state
+            } else if (__all_sync(0xffffffffu, poly_ok || !valid)) {
+                acc = fma(dps, fma(dps, fma(dps, fma(dps, c4, c3), c2), c1), acc + acc_T0);
+                // the layers around p_ref, top-down from the polynomial's upper edge (functions.py:174-179)
+                pb = p_edge;
+                const float2 *pTe = bTe - (L - 1 - ld_hi) * NT;
+                for (int l = ld_hi; l >= ld_lo; --l, pTe -= NT) {
+                    const double2 hl = s_hl[l];
+                    const double pt = fma(psn, hl.y, hl.x);
+                    const bool part = pt < pref;
+                    acc = layer(l, *pTe, part ? pref : pt, acc);
+                    pb = pt;
+                    if (part) break;
+                }
             } else {
                 // layers ltop..L-1 are entirely below p_ref for this ps; it moves by at most a level or two
                 while (ltop > lst) { const double2 h = s_hl[ltop - 1]; if (fma(psn, h.y, h.x) >= pref) --ltop; else break; }
                 while (ltop < L) { const double2 h = s_hl[ltop]; if (fma(psn, h.y, h.x) < pref) ++ltop; else break; }
                 const float2 *pTe = bTe;
                 int l = L - 1;
-#pragma unroll 4
+#pragma unroll 2
                 for (; l >= ltop; --l, pTe -= NT) {
                     const double2 hl = s_hl[l];
-                    const float2 m = s_m[l];
-                    const float2 te = *pTe;
-                    const float e = te.y;
-                    const double Td = (double)te.x;
                     const double pt = fma(psn, hl.y, hl.x);
-                    // Tv = T (1 + 0.61 hus), hus = 0.622 e / (p - 0.378 e)   (functions.py:66-72, :144)
-                    const float g = fast_rcp(fmaf(-0.378f, e, fmaf(psn_f, m.y, m.x)));
-                    const double tv = fma(Td, (double)((0.61f * 0.622f) * e * g), Td);
-                    acc = fma(tv, ln_ratio<FAST>(pb, pt, lk), acc);
+                    acc = layer(l, *pTe, pt, acc);
                     pb = pt;
                 }
-                if (l >= lst && pb >= pref) {                              // layer that contains p_ref (:174-179)
-                    const float2 m = s_m[l];
-                    const float2 te = *pTe;
-                    const float e = te.y;
-                    const double Td = (double)te.x;
-                    const float g = fast_rcp(fmaf(-0.378f, e, fmaf(psn_f, m.y, m.x)));
-                    const double tv = fma(Td, (double)((0.61f * 0.622f) * e * g), Td);
-                    acc = fma(tv, ln_ratio<FAST>(pb, pref, lk), acc);
-                }
+                if (l >= lst && pb >= pref) acc = layer(l, *pTe, pref, acc);   // layer that contains p_ref (:174-179)
             }
             const double phi_pgw = fis + kRd * acc;
             const double err = (phi_pgw - phi_era) - gdzg;
@@ -447,8 +515,8 @@ pgw_column_tma_kernel(const __grid_constant__ pgw_timestep_args a, const __grid_
             pTe[-NT] = make_float2(tp1, e1);
             pTe -= 2 * NT;
             if (j == 0) t_low_d = (double)t0 + (double)d0.ta;
-            era_layer(l, p0, t0, q0, d0.ta, tp0, e0);
-            era_layer(l - 1, p1, t1, q1, d1.ta, tp1, e1);
+            era_layer(l, p0, mm0.y, t0, q0, d0.ta, tp0, e0);
+            era_layer(l - 1, p1, mm1.y, t1, q1, d1.ta, tp1, e1);
         } else {
             sl[3 * NT] = qv_from_e(e0, psn_f, mm0);       // functions.py:66-72 with the adjusted ps
             sl[2 * NT] = qv_from_e(e1, psn_f, mm1);

@@ -568,7 +568,7 @@ pgw_column_plan plan_column(const pgw_timestep_args *a) {
     p.tma = false;
     int lst_tma = 0;
     size_t smem_tma = 0;
-    if (tma_allowed() && pgw_tma_eligible(a, p.lst, &lst_tma, &smem_tma)) {
+    if (tma_allowed() && !(a->flags & PGW_FLAG_DIRECT) && pgw_tma_eligible(a, p.lst, &lst_tma, &smem_tma)) {
         p.tma = true;
         p.lst = lst_tma;
         p.np = a->nlev - lst_tma;

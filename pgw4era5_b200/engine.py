@@ -213,7 +213,7 @@ class PGWEngine:
 
     # ------------------------------------------------------------------ submit
     def submit(self, era, era_step_dt, out=None, ignore_top_pressure_error=False, k_spec=None,
-               file_name="<memory>", slot=0):
+               file_name="<memory>", slot=0, direct=False):
         """
         Enqueue one timestep on the current CUDA stream.  ``era``: float32 CUDA
         tensors PS, FIS, FR_LAND, FR_SEA_ICE, T_SKIN [1,ny,nx], T_SO [1,S,ny,nx],
@@ -223,6 +223,8 @@ class PGWEngine:
         if settings.i_reinterp or settings.p_ref_inp is None:
             raise ValueError("i_reinterp = 1 / p_ref_inp = None run through the staged path: use apply()")
         a, f, out, ws, k_spec, k_max = self._fill_args(era, era_step_dt, out, k_spec, slot)
+        if direct:
+            a.flags |= N.FLAG_DIRECT          # every parked level integrated in every iteration
         status = ws["status"]
         base = status.data_ptr()
         result_ptr = base + 8 * N.PGW_MAX_ITER
@@ -247,7 +249,7 @@ class PGWEngine:
         ev = torch.cuda.Event()
         ev.record()
         ctx = dict(era=era, when=era_step_dt, ignore_top=ignore_top_pressure_error, k_spec=k_spec,
-                   k_max=k_max, keep=(f, a), file_name=file_name, slot=slot)
+                   k_max=k_max, keep=(f, a), file_name=file_name, slot=slot, direct=direct)
         return Pending(self, a, out, host, ev, ctx)
 
     def _fill_args(self, era, era_step_dt, out=None, k_spec=None, slot=0):
@@ -350,13 +352,15 @@ class PGWEngine:
             self.ps_bound *= 1.25
             self.stats["reruns"] += 1
             return self.submit(ctx["era"], ctx["when"], out=p.out, ignore_top_pressure_error=ctx["ignore_top"],
-                               k_spec=ctx["k_spec"], file_name=ctx["file_name"], slot=ctx["slot"]).result()
+                               k_spec=ctx["k_spec"], file_name=ctx["file_name"], slot=ctx["slot"],
+                               direct=ctx["direct"]).result()
         if not converged:
             if ctx["k_spec"] >= ctx["k_max"]:
                 raise ValueError(MSG_NOCONV.format(ctx["file_name"]))   # step_03:315-319
             self.stats["reruns"] += 1
             return self.submit(ctx["era"], ctx["when"], out=p.out, ignore_top_pressure_error=ctx["ignore_top"],
-                               k_spec=ctx["k_max"], file_name=ctx["file_name"], slot=ctx["slot"]).result()
+                               k_spec=ctx["k_max"], file_name=ctx["file_name"], slot=ctx["slot"],
+                               direct=ctx["direct"]).result()
         # predict the largest recent count: one iteration too many costs a cheap rewrite
         # (+13 % traffic), one too few a full rerun
         self._n_hist = (self._n_hist + [int(n_iter)])[-4:]

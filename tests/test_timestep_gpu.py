@@ -228,7 +228,9 @@ def test_tma_and_generic_flavours_agree(ny, nx, seed, monkeypatch):
         assert torch.equal(res_t[name].view(torch.int32), res_g[name].view(torch.int32)), name
     assert float((res_t["PS"] - res_g["PS"]).abs().max()) <= 1e-5 * 1e5 * 2 ** -23 * 4     # few fp32 ulps of ps
     assert float((res_t["QV"] - res_g["QV"]).abs().max()) <= 1e-9
-    np.testing.assert_allclose(res_t["phi_max_errors"], res_g["phi_max_errors"], rtol=1e-9)
+    # the TMA flavour sums the layers below p_ref through a polynomial in dps (truncation + fp32 humidity
+    # coefficients: a few 1e-7 m2/s2), the cp.async flavour integrates every level in every iteration
+    np.testing.assert_allclose(res_t["phi_max_errors"], res_g["phi_max_errors"], rtol=0, atol=5e-6)
 
 
 def test_odd_ncol_takes_generic_flavour():
