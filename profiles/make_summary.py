@@ -1,0 +1,68 @@
+"""Regenerate profiles/r1_summary.md from the bench logs of the last gpurun calls (gpurun_out/)."""
+import csv
+import collections
+import json
+import os
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = os.path.join(ROOT, "gpurun_out")
+last = lambda f: json.loads(open(os.path.join(G, f)).read().strip().splitlines()[-1])
+d, n2, ref = last("bench_default.log"), last("bench_n2.log"), last("bench_ref.log")
+rows = [r for r in csv.reader(open(os.path.join(ROOT, "profiles", "r1_launches.csv"))) if len(r) > 10 and r[0].isdigit()]
+c = collections.defaultdict(list)
+for r in rows:
+    c[r[4].split('(')[0].replace("void ", "")].append(float(r[-1]) / 1e3)
+tot = sum(sum(v) for v in c.values())
+launch = "; ".join("`%s` %.0f us x%d (%.1f %%)" % (k, sum(v) / len(v), len(v), 100 * sum(v) / tot) for k, v in c.items())
+step02 = json.load(open(os.path.join(ROOT, "profiles", "r1_step02.json")))
+files = json.load(open(os.path.join(ROOT, "profiles", "r1_files.json")))
+traffic = json.load(open(os.path.join(ROOT, "profiles", "column_kernel_traffic.json")))
+s = '''# Round 1 - measured numbers (B200, sm_100a, SM clock %(mhz).0f MHz, throttle reasons: %(reasons)s)
+
+All numbers from `bench.py` / `profiles/bench_*.py` on `gpurun` boxes of this pool; ncu evidence next to this file.
+Workload: BASELINE configs[1], global 0.25 degree ERA5 timestep (721x1440 columns x 137 levels, plev19 monthly deltas),
+inputs cycling through 4 distinct device-resident timesteps (2.3 GB each >> 126 MB L2).
+
+| quantity | value | source |
+|---|---|---|
+| timesteps/s, 1xB200 (`value`) | %(value).1f | `python bench.py` (%(steps)d steps) |
+| ms per timestep (whole step, 4 launches) | %(ms).3f | same |
+| column kernel, mean launch (CUDA events in the timed region) | %(kms).3f ms | same |
+| algorithmic bytes per launch (SURVEY 8d) | 5 311.6 MB | `bench.algorithmic_bytes` |
+| achieved | %(ach).0f GB/s = **%(frac).3f** of the measured peak 6 535 GB/s (%(fracn).2f of nominal 8 TB/s) | same |
+| DRAM traffic per launch (ncu `dram__bytes_read+write`) | %(tr).2f GB (%(trr).2f R + %(trw).2f W) | `r1_column_kernel.md` |
+| end to end, host buffers, H2D+D2H inside (`e2e`) | %(e2e).1f timesteps/s (2.31 GB each way per step; PCIe moves that in 49.8 ms = 20.1/s at best) | same |
+| timesteps/s, 2xB200, timestep-sharded (weak) | %(n2).1f (delta broadcast %(bc).0f ms, once) | torchrun, %(n2steps)d steps (kernel of an earlier commit of the round) |
+| CPU baseline, oracle port, 1 host core | %(cpu).4f timesteps/s | `cpu_baseline` |
+| reference arm (`--impl reference`), oracle port on %(cores)d host cores | %(ref).3f timesteps/s | `bench.py --impl reference` |
+| iteration count | 6 in %(nit)d/%(nit)d steps, %(reruns)d reruns, %(rew)d rewrites (warm-up only) | `config.n_iter`, `config.engine` |
+| step_02 smoothing, one 3-D daily variable | %(sm_ms).2f ms = %(sm_g).0f GB/s (%(sm_f).2f of peak) | `bench_step02.py`, `r1_step02.json` |
+| step_02 regridding, one 3-D daily variable (28.8 GB out) | %(rg_ms).2f ms = %(rg_g).0f GB/s (%(rg_f).2f of peak) | same |
+| file -> file, EU files (126 MB), NetCDF-3 | %(fp).1f files/s pipelined vs %(fs).1f file by file | `bench_files.py`, `r1_files.json` |
+
+Launch list of one bench run (`r1_launches.csv`, ncu `--metrics gpu__time_duration.sum --clock-control none -k regex:pgw`;
+cold-cache, serialised): %(launch)s.  `pgw_rewrite_kernel` only works in the two warm-up steps that over-predicted
+`k_spec` (~240 us), otherwise it returns at once.  The column kernel's share of the step agrees with the event timing.
+
+Kernel history of the round (global/plev19, ms per column-kernel launch): 9.0 (first fused pass) -> 3.5 (cp.async ring,
+shared-log walkers) -> 2.6 (fp32 stash, 3 CTAs/SM) -> 2.2 (batched prologue, node prefetch) -> 2.08 (paired levels) ->
+1.99 (L2 node prefetch, iteration 0 folded into phase 1, consume-before-load walker steps) -> 1.69 (TMA pair ring with a
+producer warp, one float4 walker, one streaming loop: hot code 4 900 -> 600 SASS instructions, icache hit 94 -> 99.4 %%) ->
+1.63 (prefetch distances, incremental node offsets) -> 1.47 (fixed point through a polynomial in dps: the parked levels
+are integrated once, not once per iteration).
+
+Tools: `summarize_ncu.py` (report -> markdown), `line_profile.py` (per-source-line instructions / stall samples, joins the
+ncu SASS page with `nvdisasm -g`), `gpu_cycle.sh` (tests + bench + capture in one `gpurun` call), `build_variant.sh`
+(A/B builds selected with `PGW_B200_LIB`), `make_summary.py` (this file).
+''' % dict(mhz=d["clocks"]["sm_mhz"], reasons=d["clocks"]["reasons"] or "none", value=d["value"], steps=d["steps"],
+           ms=d["ms_per_step"], kms=d["roofline"]["kernel_ms"], ach=d["roofline"]["achieved"], frac=d["roofline"]["frac"],
+           fracn=d["roofline"]["achieved"] / 8000.0, tr=traffic["dram_bytes_per_launch"] / 1e9,
+           trr=traffic["dram_read"] / 1e9, trw=traffic["dram_write"] / 1e9, e2e=d["e2e"]["value"], n2=n2["value"],
+           bc=n2["config"]["broadcast_ms"], n2steps=n2["steps"], cpu=d["cpu_baseline"]["value"],
+           cores=ref["cpu_baseline"]["cores"], ref=ref["value"], nit=d["config"]["n_iter"]["steps"],
+           reruns=d["config"]["engine"]["reruns"], rew=d["config"]["engine"]["rewrites"],
+           sm_ms=step02["smoothing"]["ms"], sm_g=step02["smoothing"]["achieved_gbs"], sm_f=step02["smoothing"]["frac_of_peak"],
+           rg_ms=step02["regridding"]["ms"], rg_g=step02["regridding"]["achieved_gbs"], rg_f=step02["regridding"]["frac_of_peak"],
+           fp=files["pipelined_files_per_s"], fs=files["file_by_file_files_per_s"], launch=launch)
+open(os.path.join(ROOT, "profiles", "r1_summary.md"), "w").write(s)
+print(s)
