@@ -8,6 +8,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G = os.path.join(ROOT, "gpurun_out")
 last = lambda f: json.loads(open(os.path.join(G, f)).read().strip().splitlines()[-1])
 d, n2, ref = last("bench_default.log"), last("bench_n2.log"), last("bench_ref.log")
+n8 = last("bench_n8.log")
 rows = [r for r in csv.reader(open(os.path.join(ROOT, "profiles", "r1_launches.csv"))) if len(r) > 10 and r[0].isdigit()]
 c = collections.defaultdict(list)
 for r in rows:
@@ -33,6 +34,7 @@ inputs cycling through 4 distinct device-resident timesteps (2.3 GB each >> 126 
 | DRAM traffic per launch (ncu `dram__bytes_read+write`) | %(tr).2f GB (%(trr).2f R + %(trw).2f W) | `r1_column_kernel.md` |
 | end to end, host buffers, H2D+D2H inside (`e2e`) | %(e2e).1f timesteps/s (2.31 GB each way per step; PCIe moves that in 49.8 ms = 20.1/s at best) | same |
 | timesteps/s, 2xB200, timestep-sharded (weak) | %(n2).1f (delta broadcast %(bc).0f ms, once) | torchrun, %(n2steps)d steps (kernel of an earlier commit of the round) |
+| timesteps/s, 8xB200, timestep-sharded (weak) | %(n8).1f = 8 x %(n8p).1f (delta broadcast %(bc8).0f ms, once; BASELINE target: >= 4 922) | torchrun, %(n8steps)d steps per rank |
 | CPU baseline, oracle port, 1 host core | %(cpu).4f timesteps/s | `cpu_baseline` |
 | reference arm (`--impl reference`), oracle port on %(cores)d host cores | %(ref).3f timesteps/s | `bench.py --impl reference` |
 | iteration count | 6 in %(nit)d/%(nit)d steps, %(reruns)d reruns, %(rew)d rewrites (warm-up only) | `config.n_iter`, `config.engine` |
@@ -58,7 +60,7 @@ ncu SASS page with `nvdisasm -g`), `gpu_cycle.sh` (tests + bench + capture in on
            ms=d["ms_per_step"], kms=d["roofline"]["kernel_ms"], ach=d["roofline"]["achieved"], frac=d["roofline"]["frac"],
            fracn=d["roofline"]["achieved"] / 8000.0, tr=traffic["dram_bytes_per_launch"] / 1e9,
            trr=traffic["dram_read"] / 1e9, trw=traffic["dram_write"] / 1e9, e2e=d["e2e"]["value"], n2=n2["value"],
-           bc=n2["config"]["broadcast_ms"], n2steps=n2["steps"], cpu=d["cpu_baseline"]["value"],
+           bc=n2["config"]["broadcast_ms"], n8=n8["value"], n8p=n8["value"] / 8, bc8=n8["config"]["broadcast_ms"], n8steps=n8["steps"], n2steps=n2["steps"], cpu=d["cpu_baseline"]["value"],
            cores=ref["cpu_baseline"]["cores"], ref=ref["value"], nit=d["config"]["n_iter"]["steps"],
            reruns=d["config"]["engine"]["reruns"], rew=d["config"]["engine"]["rewrites"],
            sm_ms=step02["smoothing"]["ms"], sm_g=step02["smoothing"]["achieved_gbs"], sm_f=step02["smoothing"]["frac_of_peak"],
