@@ -269,3 +269,45 @@ def test_staged_path_equals_fused_for_default_settings():
     assert res_s["n_iter"] == res_f["n_iter"]
     for name in ("PS", "T", "QV", "U", "V", "T_SKIN", "T_SO", "FR_SEA_ICE"):
         assert float((res_s[name] - fused[name]).abs().nan_to_num().max()) <= TOL[name], name
+
+
+def _flat_case(ny, nx, seed, zscale):
+    """A case with the orography scaled down (so that a high p_ref stays above the ground)."""
+    from pgw4era5_b200.constants import CON_RD
+    era, deltas = make_case(ny, nx, seed)
+    era["FIS"] = era["FIS"] * zscale
+    era["PS"] = (101325.0 * torch.exp(-era["FIS"].double() / (CON_RD * 270.0))).float()
+    deltas["ps_hist"]["data"] = era["PS"].expand_as(deltas["ps_hist"]["data"]).clone() * 1.002
+    return era, deltas
+
+
+@pytest.mark.parametrize("p_ref", [85000, 50000, 10000])
+def test_polynomial_fixed_point_other_reference_pressures(p_ref):
+    """TMA flavour (ncol % 4 == 0): p_ref two layers above the ground (almost no layer in the polynomial,
+    l* + 1 == the lowest level for some columns), mid troposphere, and 100 hPa (91 parked levels: the
+    stash no longer allows 3 CTAs/SM) against the oracle."""
+    from pgw4era5_b200 import settings
+    era, deltas = _flat_case(12, 24, 31, 0.05)
+    ref = run_oracle(era, deltas, p_ref_inp=p_ref)
+    old = settings.p_ref_inp
+    settings.p_ref_inp = p_ref
+    try:
+        res, eng = _apply(era, deltas)
+        assert _uses_tma(eng, era) == 1
+    finally:
+        settings.p_ref_inp = old
+    np.testing.assert_allclose(res["phi_max_errors"], ref["phi_max_errors"], rtol=0, atol=1e-3)
+    _check(res, ref)
+
+
+def test_polynomial_fixed_point_large_ps_change_falls_back():
+    """zg deltas ten times larger: |dps| reaches several thousand Pa, beyond the range of the polynomial
+    (0.012 ps), so warps integrate all parked levels directly; results still match the oracle."""
+    era, deltas = make_case(12, 24, 33)
+    deltas["zg"]["data"] = deltas["zg"]["data"] * 10.0
+    ref = run_oracle(era, deltas)
+    assert float(np.abs(ref["deltas"]["ps"]).max()) > 0.012 * 101325
+    res, eng = _apply(era, deltas)
+    assert _uses_tma(eng, era) == 1
+    np.testing.assert_allclose(res["phi_max_errors"], ref["phi_max_errors"], rtol=0, atol=1e-3)
+    _check(res, ref)
