@@ -128,11 +128,17 @@ def cpu_arm(n_tasks, procs, rows=8, nx=1440, pool=None):
     tasks = [(1000 + i, rows, nx) for i in range(n_tasks)]
     t0 = time.perf_counter()
     if pool is not None:
-        pool.map(_cpu_sample, tasks, chunksize=1)
+        res = pool.map(_cpu_sample, tasks, chunksize=1)
     else:
-        for t in tasks:
-            _cpu_sample(t)
+        res = [_cpu_sample(t) for t in tasks]
     wall = time.perf_counter() - t0
+    # time of the reference path only (the synthetic inputs are generated outside it): the slowest
+    # worker when every worker holds one band, the sum on one core
+    comp = [r[0] for r in res]
+    if pool is None:
+        wall = sum(comp)
+    elif n_tasks <= procs:
+        wall = max(comp)
     cols = n_tasks * rows * nx
     ts = cols / float(GRIDS["GL"][0] * GRIDS["GL"][1])
     return ts / wall, wall, cols
@@ -150,11 +156,16 @@ def run_reference(a):
     procs = max(1, os.cpu_count() or 1)
     procs = min(procs, 64)
     steps = max(1, a.steps)
-    rows = 8
     ctx = mp.get_context("spawn")
     vals, walls = [], []
     with ctx.Pool(procs) as pool:
         pool.map(_cpu_sample, [(1, 2, 64)] * procs, chunksize=1)     # start workers, imports
+        # bounded sample: bands of `rows` x 1440 columns per worker and step, sized so that the whole
+        # --steps/--warmup run stays within about three minutes (one calibration step with 2 rows)
+        t_cal = time.perf_counter()
+        cpu_arm(procs, procs, 2, pool=pool)
+        t_cal = time.perf_counter() - t_cal
+        rows = int(max(1, min(8, 2 * 180.0 / (t_cal * (steps + max(a.warmup, 0))))))
         for _ in range(max(a.warmup, 0)):
             cpu_arm(procs, procs, rows, pool=pool)
         for _ in range(steps):
