@@ -22,6 +22,11 @@
 // the ta/hur columns only matters below the node under ps_hist, where it is applied as an override.
 // Both keep the hot code small: the previous version was instruction-cache bound.
 //
+// The fixed point does not re-integrate the parked levels in every iteration: their geopotential sum is
+// expanded once, during the sweep, as a polynomial in dps (see "the geopotential sums of the parked
+// levels" below); only the three layers around p_ref are integrated per iteration, and a warp whose
+// dps leaves the range of the polynomial falls back to the full integration for that iteration.
+//
 // Needs ncol % 4 == 0 (16-byte global strides), 16-byte aligned fields and nlev <= kTmaMaxLev;
 // anything else takes the cp.async flavour.
 #include "pgw_column.cuh"
