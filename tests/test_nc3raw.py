@@ -1,0 +1,66 @@
+"""The raw NetCDF-3 access of the file pipeline (pgw4era5_b200/nc3raw.py) against scipy's reader."""
+import os
+
+import numpy as np
+import pytest
+
+from pgw4era5_b200 import ncio
+from pgw4era5_b200.nc3raw import NC_FLOAT, NotNetCDF3, RawNC3
+
+
+def _make(path, nt=1):
+    rng = np.random.default_rng(5)
+    ds = ncio.Dataset()
+    ds["time"] = ncio.Variable(("time",), np.arange(nt, dtype=np.float64), {"units": "hours since 2006-08-01 00:00:00"})
+    ds["lat"] = ncio.Variable(("lat",), np.linspace(30, 80, 5)); ds["lon"] = ncio.Variable(("lon",), np.arange(7.0))
+    ds["level"] = ncio.Variable(("level",), np.arange(1.0, 4.0))
+    ds["ak"] = ncio.Variable(("level",), rng.normal(size=3))
+    ds["PS"] = ncio.Variable(("time", "lat", "lon"), rng.normal(size=(nt, 5, 7)).astype(np.float32), {"units": "Pa"})
+    ds["T"] = ncio.Variable(("time", "level", "lat", "lon"), rng.normal(size=(nt, 3, 5, 7)).astype(np.float32))
+    ds["FIS"] = ncio.Variable(("lat", "lon"), rng.normal(size=(5, 7)).astype(np.float32))
+    ds["count"] = ncio.Variable(("time",), np.arange(nt, dtype=np.int32))
+    ds.attrs["title"] = "raw access test"
+    ds.to_netcdf(path)
+    return ds
+
+
+@pytest.mark.parametrize("nt", [1, 3])
+def test_header_and_raw_reads_match_scipy(tmp_path, nt):
+    path = str(tmp_path / "a.nc")
+    ds = _make(path, nt)
+    raw = RawNC3(path)
+    assert raw.numrecs == nt and raw.dims["lat"] == 5 and raw.dims["time"] == nt
+    assert raw.vars["T"].nc_type == NC_FLOAT and raw.vars["T"].is_record and not raw.vars["FIS"].is_record
+    assert raw.vars["T"].shape == (nt, 3, 5, 7) and raw.vars["T"].record_shape == (3, 5, 7)
+    with open(path, "rb", buffering=0) as f:
+        for name in ("PS", "T", "FIS", "ak"):
+            v = raw.vars[name]
+            for rec in range(nt if v.is_record else 1):
+                buf = np.empty(v.record_shape, dtype=v.dtype)
+                raw.read_into(f, name, buf, record=rec)
+                want = ds[name].data[rec] if v.is_record else ds[name].data
+                np.testing.assert_array_equal(buf.astype(buf.dtype.newbyteorder("=")), want)
+
+
+def test_patch_in_place(tmp_path):
+    path = str(tmp_path / "b.nc")
+    ds = _make(path, 2)
+    raw = RawNC3(path)
+    new = (np.arange(3 * 5 * 7, dtype=np.float32).reshape(3, 5, 7) + 0.5).astype(">f4")
+    fd = os.open(path, os.O_RDWR)
+    try:
+        raw.write_from(fd, "T", new, record=1)
+    finally:
+        os.close(fd)
+    back = ncio.open_dataset(path)
+    np.testing.assert_array_equal(back["T"].data[1], new.astype(np.float32))
+    np.testing.assert_array_equal(back["T"].data[0], ds["T"].data[0])          # the other record is untouched
+    np.testing.assert_array_equal(back["PS"].data, ds["PS"].data)
+    assert back["PS"].attrs["units"] == "Pa" and back.attrs["title"] == "raw access test"
+
+
+def test_rejects_other_files(tmp_path):
+    p = tmp_path / "c.nc"
+    p.write_bytes(b"\x89HDF\r\n\x1a\n" + b"\0" * 64)
+    with pytest.raises(NotNetCDF3):
+        RawNC3(str(p))
