@@ -97,10 +97,12 @@ def saturation_vapor_pressure_water_and_ice(pa, ta):
     """functions.py:91-105 (IFS 7.92): alpha blend of water and ice."""
     T0 = 273.16
     Ti = 250.16
-    ta = np.asarray(ta, dtype=np.float64)
+    ta = np.asarray(ta)                  # the dtype of ta is kept, as in the reference
+    if ta.dtype.kind != "f":
+        ta = ta.astype(np.float64)
     alpha = np.full_like(ta, np.nan)
-    alpha = np.where(ta >= T0, 1.0, alpha)
-    alpha = np.where(ta <= Ti, 0.0, alpha)
+    alpha = np.where(ta >= T0, 1, alpha)
+    alpha = np.where(ta <= Ti, 0, alpha)
     with np.errstate(invalid="ignore"):
         alpha = np.where((ta < T0) & (ta > Ti),
                          np.power((ta - Ti) / (T0 - Ti), 2.), alpha)
@@ -123,23 +125,30 @@ def relative_to_specific_humidity(hur, pa, ta):
 # ---------------------------------------------------------------------------
 # geopotential (functions.py:128-189)
 # ---------------------------------------------------------------------------
-def integ_geopot(pa_hl, zgs, ta, hus, p_ref):
+def integ_geopot(pa_hl, zgs, ta, hus, p_ref, phi_dtype=np.float64):
     """
     functions.py:128-189.  pa_hl [nt,L+1,ny,nx], zgs [nt,ny,nx], ta/hus
     [nt,L,ny,nx], p_ref scalar or [nt,ny,nx].  Half-level labels are assumed
     1..L+1 and full-level labels 1..L (so ``level = hl_ref_star - 1`` is the
     layer just above the selected half level, functions.py:176).
+
+    dtypes as in the reference, where they follow from numpy's promotion rules: ``ta``/``hus`` are
+    NOT promoted -- with the float32 fields of an ERA5 file, ``tav`` (:144) and ``CON_RD * tav``
+    (:151, :177) are float32 products, with the float64 PGW state they are float64.  ``phi_dtype``
+    is the dtype the half-level geopotential is stored in (:141 copies the dtype of FIS: float32
+    for a real ERA5 file; float64, the default here, when FIS is stored as double).
+    Pinned by tests/test_oracle_glue_golden.py against the reference executed over oracle/xrlite.py.
     """
     pa_hl = np.asarray(pa_hl, dtype=np.float64)
-    ta = np.asarray(ta, dtype=np.float64)
-    hus = np.asarray(hus, dtype=np.float64)
-    zgs = np.asarray(zgs, dtype=np.float64)
+    ta = np.asarray(ta)
+    hus = np.asarray(hus)
+    zgs = np.asarray(zgs)
     pa_hl = np.where(pa_hl > 0, pa_hl, 0.0001)              # :135
     lnp = np.log(pa_hl)
     dlnpa = lnp[:, 1:] - lnp[:, :-1]                         # :136-138
     tav = ta * (1 + 0.61 * hus)                              # :144
     nl = ta.shape[1]
-    phi_hl = np.empty_like(pa_hl)
+    phi_hl = np.empty(pa_hl.shape, dtype=phi_dtype)
     phi_hl[:, nl] = zgs                                      # :141
     for l in range(nl - 1, -1, -1):                          # :147-152
         phi_hl[:, l] = phi_hl[:, l + 1] + (CON_RD * tav[:, l] * dlnpa[:, l])
@@ -534,7 +543,8 @@ def regrid_lat_lon(data, lat_gcm, lon_gcm, targ_lat, targ_lon):
 # ---------------------------------------------------------------------------
 def pgw_for_era5(era, deltas, era_step_dt, *, p_ref_inp=30000, adj_factor=0.95,
                  thresh_phi_ref_max_error=0.15, max_n_iter=20,
-                 ignore_top_pressure_error=False, n_iter_fixed=None, i_reinterp=0):
+                 ignore_top_pressure_error=False, n_iter_fixed=None, i_reinterp=0,
+                 emulate_file_dtypes=False):
     """
     step_03_apply_to_era.py:44-381.  ``i_reinterp`` (settings.py:150) re-interpolates the ERA
     state and the deltas onto the updated model levels every iteration (:202-216, :330-343);
@@ -549,15 +559,29 @@ def pgw_for_era5(era, deltas, era_step_dt, *, p_ref_inp=30000, adj_factor=0.95,
     Returns dict with PS,T,QV,U,V,T_SKIN,T_SO,FR_SEA_ICE (float64), 'n_iter',
     'phi_max_errors' (one per iteration) and 'deltas' (interpolate_full taps).
 
+    dtypes.  The reference never casts: what it computes in follows from the dtypes of the ERA5 file
+    through numpy's promotion rules (found by executing it over oracle/xrlite.py, see
+    oracle/make_golden_glue.py).  Always reproduced here: the virtual temperature of the ERA state is a
+    product of the float32 T and QV (functions.py:144), the PGW state is float64.  Reproduced with
+    ``emulate_file_dtypes=True``, for PS/FIS/T/QV passed in as float32 like in a real ERA5 file:
+    ``delta_ps`` and hence ``ps_pgw`` are float32 (xarray's in-place ``+=`` keeps the dtype of
+    zeros_like(PS), :186-195), the half-level geopotential is stored as float32 (functions.py:141)
+    and RELHUM of the ERA state is evaluated in float32 (:91-94).  These add rounding noise of
+    ~2e-2 m2/s2 to the geopotential error and ~3e-2 Pa to ps_pgw; a threshold below ~1e-2 m2/s2 can
+    then not be met.  The default (False) models PS and FIS stored as double and RELHUM in float64.
+
     n_iter_fixed (test hook, not in the reference): run exactly that many iterations
     regardless of the threshold and also return 'ps_traj' (ps after each iteration's
     update); used to check the latitude-band scheme in which the stopping rule is
     evaluated on the MAX over all bands.
     """
     f64 = lambda a: np.asarray(a, dtype=np.float64)
+    asis = (lambda a: np.asarray(a)) if emulate_file_dtypes else f64
     ak, bk = f64(era["ak"]), f64(era["bk"])
-    PS = f64(era["PS"])
-    T, QV, U, V = f64(era["T"]), f64(era["QV"]), f64(era["U"]), f64(era["V"])
+    PS = asis(era["PS"])
+    FIS = asis(era["FIS"])
+    T, QV = np.asarray(era["T"]), np.asarray(era["QV"])      # dtype of the file (see above)
+    U, V = f64(era["U"]), f64(era["V"])
     lev = lambda c: c[None, :, None, None]
     pa_hl_era = lev(ak) + PS[:, None] * lev(bk)              # :64-66
     if "akm" in era:                                         # :68-85
@@ -566,7 +590,8 @@ def pgw_for_era5(era, deltas, era_step_dt, *, p_ref_inp=30000, adj_factor=0.95,
         akm = 0.5 * np.diff(ak) + ak[:-1]
         bkm = 0.5 * np.diff(bk) + bk[:-1]
     pa_era = lev(akm) + PS[:, None] * lev(bkm)               # :87-88
-    RELHUM = specific_to_relative_humidity(QV, pa_era, T)    # :91-94
+    with np.errstate(all="ignore"):
+        RELHUM = specific_to_relative_humidity(asis(QV), pa_era, asis(T))    # :91-94
 
     # ---- surface and soil (:103-146); ERA5 fields are float32 in the file and
     # updated in place there; the oracle keeps float64.
@@ -604,7 +629,7 @@ def pgw_for_era5(era, deltas, era_step_dt, *, p_ref_inp=30000, adj_factor=0.95,
             vars_pgw[var] = vars_era[var] + dv
 
     # ---- iterative surface-pressure adjustment (:182-319)
-    delta_ps = np.zeros_like(PS)
+    delta_ps = np.zeros_like(PS)                             # dtype of PS (:186)
     adj_ps = np.zeros_like(PS)
     phi_ref_max_error = np.inf
     errs = []
@@ -614,7 +639,7 @@ def pgw_for_era5(era, deltas, era_step_dt, *, p_ref_inp=30000, adj_factor=0.95,
     ps_traj, hus_traj = [], []
     while (phi_ref_max_error > thresh_phi_ref_max_error if n_iter_fixed is None
            else it <= n_iter_fixed):
-        delta_ps = delta_ps + adj_ps
+        delta_ps = (delta_ps + adj_ps).astype(delta_ps.dtype)   # in place in the reference (:194)
         ps_pgw = PS + delta_ps
         pa_pgw = lev(akm) + ps_pgw[:, None] * lev(bkm)
         pa_hl_pgw = lev(ak) + ps_pgw[:, None] * lev(bk)
@@ -640,9 +665,9 @@ def pgw_for_era5(era, deltas, era_step_dt, *, p_ref_inp=30000, adj_factor=0.95,
             p_ref = p_ref_inp
         vars_pgw["hus"] = relative_to_specific_humidity(
             vars_pgw["hur"], pa_pgw, vars_pgw["ta"])
-        phi_ref_pgw = integ_geopot(pa_hl_pgw, f64(era["FIS"]), vars_pgw["ta"],
-                                   vars_pgw["hus"], p_ref)
-        phi_ref_era = integ_geopot(pa_hl_era, f64(era["FIS"]), T, QV, p_ref)
+        phi_ref_pgw = integ_geopot(pa_hl_pgw, FIS, vars_pgw["ta"],
+                                   vars_pgw["hus"], p_ref, FIS.dtype)
+        phi_ref_era = integ_geopot(pa_hl_era, FIS, T, QV, p_ref, FIS.dtype)
         delta_phi_ref = phi_ref_pgw - phi_ref_era
         dzg = load_delta(deltas["zg"], era_step_dt) * CON_G  # :292-295
         if p_ref_inp is None:                                # .sel(plev=p_ref), pointwise

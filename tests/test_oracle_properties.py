@@ -62,7 +62,9 @@ def test_zero_deltas_one_iteration_identity():
         v["data"].zero_()
     deltas["ps_hist"]["data"] += era["PS"]
     ref = run_oracle(era, deltas)
-    assert ref["n_iter"] == 1 and ref["phi_max_errors"][0] < 1e-6
+    # not ~0: the reference multiplies the float32 T and QV of the ERA state in float32 (functions.py:144),
+    # the float64 PGW state in float64 (reproduced by the oracle, pinned in test_oracle_glue_golden.py)
+    assert ref["n_iter"] == 1 and ref["phi_max_errors"][0] < 2e-2
     e = S.to_numpy(era)
     np.testing.assert_array_equal(ref["PS"], e["PS"].astype(np.float64))
     np.testing.assert_array_equal(ref["T"], e["T"].astype(np.float64))
