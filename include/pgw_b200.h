@@ -145,6 +145,11 @@ int pgw_integ_geopot_f32(const float *pa_hl, const float *zgs, const float *ta, 
 int pgw_integ_geopot_f64(const double *pa_hl, const double *zgs, const double *ta, const double *hus,
                          const double *p_ref_field, double p_ref, double *phi_ref,
                          int nlev, long long ncol, uint32_t *err, void *stream);
+/* float64 pressures with the float32 T and QV of an ERA5 file: like numpy in the reference, Rd * Tv is
+ * then a chain of float32 products (functions.py:144, :151, :177), the sums are float64 */
+int pgw_integ_geopot_f64_f32(const double *pa_hl, const double *zgs, const float *ta, const float *hus,
+                             const double *p_ref_field, double p_ref, double *phi_ref,
+                             int nlev, long long ncol, uint32_t *err, void *stream);
 
 /* ------------------------------------------------------------------------
  * Land / sea-ice weighted blend of the ts and tos deltas.

@@ -82,6 +82,7 @@ def _load():
         "pgw_replace_delta_sfc_f64": (i, [vp, vp, vp, vp, vp, vp, i, ll, i, vp, vp]),
         "pgw_integ_geopot_f32": (i, [vp, vp, vp, vp, vp, d, vp, i, ll, vp, vp]),
         "pgw_integ_geopot_f64": (i, [vp, vp, vp, vp, vp, d, vp, i, ll, vp, vp]),
+        "pgw_integ_geopot_f64_f32": (i, [vp, vp, vp, vp, vp, d, vp, i, ll, vp, vp]),
         "pgw_integrate_tos_f32": (i, [vp, vp, vp, vp, vp, ll, vp]),
         "pgw_integrate_tos_f64": (i, [vp, vp, vp, vp, vp, ll, vp]),
         "pgw_time_interp_f32": (i, [vp, vp, d, d, vp, ll, vp]),

@@ -365,12 +365,12 @@ pgw_column_tma_kernel(const __grid_constant__ pgw_timestep_args a, const __grid_
             double pt = Pt;
             if (pt < pref) { pt = pref; era_open = false; lstar = l; }   // layer that contains p_ref (:174-179)
             const double td = (double)t, tpd = (double)t_pgw;
-            const double tv = fma(td, 0.61 * (double)q, td);
+            const double rtv = rd_tv(t, q);                          // Rd * Tv of the ERA state, float32 products
             const float g = fast_rcp(fmaf(-0.378f, e_pgw, p));
             const float hq_t = (0.61f * 0.622f) * e_pgw * g;         // (Tv - T) / T of the PGW state
             const double tvp = fma(tpd, (double)hq_t, tpd);
             const double dl = ln_ratio<FAST>(pb_era, pt, lk);
-            acc_era = fma(tv, dl, acc_era);
+            acc_era = fma(rtv, dl, acc_era);
             acc_res = fma((td + (double)dta) - tpd, dl, acc_res);
             if (era_open) {
                 acc_T0 = fma(tvp, dl, acc_T0);
@@ -387,7 +387,7 @@ pgw_column_tma_kernel(const __grid_constant__ pgw_timestep_args a, const __grid_
     // streamed pairs; the TMA loads of the next pairs are in flight meanwhile.
     auto fixed_point = [&]() {
         const double fis = (double)r_fis;
-        const double phi_era = fis + kRd * acc_era;
+        const double phi_era = fis + acc_era;                            // acc_era holds Rd * Tv * dlnp
         const double gdzg = blend_f64(a.zg_ref, r_zg) * kG;              // step_03:292-295
         const float2 *const bTe = st_Te + (size_t)(L - 1 - lst) * NT + tid;  // lowest level of the stash
         const double t_low = t_low_d;                                 // ta_pgw on the lowest level

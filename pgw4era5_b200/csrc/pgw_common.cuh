@@ -17,6 +17,16 @@ constexpr double kRd = 287.05;
 constexpr double kG = 9.80665;
 constexpr double kMwMd = 0.622;
 
+// Rd * Tv the way the reference forms it: tav = ta * (1 + 0.61 * hus) (functions.py:144) and
+// CON_RD * tav (:151, :177) are numpy products in the dtype of ta and hus -- float32, each product
+// rounded, for the float32 T and QV of an ERA5 file; float64 for the float64 PGW state.  Found by
+// executing the reference (oracle/make_golden_glue.py); it shifts phi(p_ref) of the ERA state by up to
+// ~4e-3 m2/s2, i.e. ps by ~7e-3 Pa, against an all-float64 evaluation.
+__device__ __forceinline__ double rd_tv(float t, float q) {
+    return (double)__fmul_rn(287.05f, __fmul_rn(t, __fadd_rn(1.0f, __fmul_rn(0.61f, q))));
+}
+__device__ __forceinline__ double rd_tv(double t, double q) { return kRd * (t * (1.0 + 0.61 * q)); }
+
 // ---------------------------------------------------------------------------
 // IFS saturation vapour pressure, functions.py:74-105.  Generic (exact formula
 // in the working precision; used by the standalone conversions).

@@ -108,10 +108,12 @@ __global__ void rh2q_kernel(const T *__restrict__ hur, const T *__restrict__ pa,
 // Pass 1 finds the half level with the smallest non-negative p_hl - p_ref
 // (first occurrence, like argmin); pass 2 integrates from the surface up to it.
 // ---------------------------------------------------------------------------
-template <typename T>
+// T: type of the pressures, zgs and p_ref; TS: type of ta and hus -- Rd * Tv is formed in TS like in
+// the reference (rd_tv in pgw_common.cuh), everything else in float64.
+template <typename T, typename TS>
 __global__ void __launch_bounds__(128)
-integ_geopot_kernel(const T *__restrict__ pa_hl, const T *__restrict__ zgs, const T *__restrict__ ta,
-                    const T *__restrict__ hus, const T *__restrict__ p_ref_field, double p_ref_scalar,
+integ_geopot_kernel(const T *__restrict__ pa_hl, const T *__restrict__ zgs, const TS *__restrict__ ta,
+                    const TS *__restrict__ hus, const T *__restrict__ p_ref_field, double p_ref_scalar,
                     double *__restrict__ phi_ref, int nlev, long long ncol, uint32_t *err) {
     const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= ncol) return;
@@ -133,14 +135,12 @@ integ_geopot_kernel(const T *__restrict__ pa_hl, const T *__restrict__ zgs, cons
         double p_up = (double)pa_hl[(long long)l * ncol + c];
         if (!(p_up > 0.0)) p_up = 0.0001;
         const double ln_up = log(p_up);
-        const double tav = (double)ta[(long long)l * ncol + c] * (1.0 + 0.61 * (double)hus[(long long)l * ncol + c]);
-        phi = phi + kRd * tav * (ln_lo - ln_up);
+        phi = phi + rd_tv(ta[(long long)l * ncol + c], hus[(long long)l * ncol + c]) * (ln_lo - ln_up);
         ln_lo = ln_up;
     }
     if (hstar < 1) { phi_ref[c] = NAN; return; }                  // no full level above (KeyError in xarray)
-    const double tav_star = (double)ta[(long long)(hstar - 1) * ncol + c] *
-                            (1.0 + 0.61 * (double)hus[(long long)(hstar - 1) * ncol + c]);
-    phi_ref[c] = phi - (kRd * tav_star) * (log(p_ref) - ln_lo);   // :174-179
+    const double rtv_star = rd_tv(ta[(long long)(hstar - 1) * ncol + c], hus[(long long)(hstar - 1) * ncol + c]);
+    phi_ref[c] = phi - rtv_star * (log(p_ref) - ln_lo);           // :174-179
 }
 
 // ---------------------------------------------------------------------------
@@ -288,16 +288,17 @@ PGW_EW3(pgw_specific_to_relative_humidity_f64, q2rh_kernel, double)
 PGW_EW3(pgw_relative_to_specific_humidity_f32, rh2q_kernel, float)
 PGW_EW3(pgw_relative_to_specific_humidity_f64, rh2q_kernel, double)
 
-#define PGW_GEOPOT(NAME, T)                                                                          \
-    int NAME(const T *pa_hl, const T *zgs, const T *ta, const T *hus, const T *p_ref_field,          \
+#define PGW_GEOPOT(NAME, T, TS)                                                                      \
+    int NAME(const T *pa_hl, const T *zgs, const TS *ta, const TS *hus, const T *p_ref_field,        \
              double p_ref, double *phi_ref, int nlev, long long ncol, uint32_t *err, void *stream) { \
         PGW_REQUIRE(pa_hl && zgs && ta && hus && phi_ref && err && nlev >= 1 && ncol > 0);           \
-        integ_geopot_kernel<T><<<(unsigned)((ncol + 127) / 128), 128, 0, (cudaStream_t)stream>>>(    \
+        integ_geopot_kernel<T, TS><<<(unsigned)((ncol + 127) / 128), 128, 0, (cudaStream_t)stream>>>(\
             pa_hl, zgs, ta, hus, p_ref_field, p_ref, phi_ref, nlev, ncol, err);                      \
         return pgw_check_launch("integ_geopot_kernel");                                              \
     }
-PGW_GEOPOT(pgw_integ_geopot_f32, float)
-PGW_GEOPOT(pgw_integ_geopot_f64, double)
+PGW_GEOPOT(pgw_integ_geopot_f32, float, float)
+PGW_GEOPOT(pgw_integ_geopot_f64, double, double)
+PGW_GEOPOT(pgw_integ_geopot_f64_f32, double, float)
 
 #define PGW_TOS(NAME, T)                                                                             \
     int NAME(const T *tos, const T *ts, const T *land, const T *ice, T *out, long long n,            \

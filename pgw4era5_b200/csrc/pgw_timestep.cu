@@ -278,11 +278,11 @@ pgw_column_kernel(const __grid_constant__ pgw_timestep_args a, const int lst, co
                 double pt = fma(PSd, hl.y, hl.x);
                 if (pt < pref) { pt = pref; era_open = false; }     // layer that contains p_ref (:174-179)
                 const double td = (double)t, tpd = (double)t_pgw;
-                const double tv = fma(td, 0.61 * (double)q, td);
+                const double rtv = rd_tv(t, q);                      // Rd * Tv of the ERA state, float32 products
                 const float g = fast_rcp(fmaf(-0.378f, e_pgw, p));
                 const double tvp = fma(tpd, (double)((0.61f * 0.622f) * e_pgw * g), tpd);
                 const double dl = ln_ratio<FAST>(pb_era, pt, lk);
-                acc_era = fma(tv, dl, acc_era);
+                acc_era = fma(rtv, dl, acc_era);
                 acc_pgw0 = fma(tvp, dl, acc_pgw0);
                 acc_res = fma((td + (double)dta) - tpd, dl, acc_res);
                 pb_era = pt;
@@ -332,7 +332,7 @@ pgw_column_kernel(const __grid_constant__ pgw_timestep_args a, const int lst, co
         }
     }
     const double fis = (double)r_fis;
-    const double phi_era = fis + kRd * acc_era;
+    const double phi_era = fis + acc_era;                            // acc_era holds Rd * Tv * dlnp
     const double gdzg = blend_f64(a.zg_ref, r_zg) * kG;              // step_03:292-295
     const float2 *const bTe = st_Te + (size_t)(L - 1 - lst) * NT + tid;  // lowest level of the stash
     const double t_low = t_low_d;                                 // ta_pgw on the lowest level

@@ -167,9 +167,12 @@ def integ_geopot(pa_hl, zgs, ta, hus, level1=None, p_ref=30000):
     functions.py:128-189.  pa_hl [nt, L+1, ny, nx], zgs [nt, ny, nx], ta/hus [nt, L, ny, nx],
     p_ref scalar or [nt, ny, nx].  ``level1`` (the half-level labels) is accepted for
     signature compatibility; labels 1..L+1 are assumed.  Returns float64 [nt, ny, nx].
+    float32 ``ta`` and ``hus`` with float64 pressures are not promoted: like numpy in the reference,
+    Rd * Tv is then formed in float32 (functions.py:144, :151).
     """
     dt = _work_dtype(pa_hl, ta, hus)
-    ph, td, qd = _dev(pa_hl, dt), _dev(ta, dt), _dev(hus, dt)
+    dts = torch.float32 if _work_dtype(ta, hus) == torch.float32 else dt
+    ph, td, qd = _dev(pa_hl, dt), _dev(ta, dts), _dev(hus, dts)
     if ph.dim() != 4:
         raise ValueError("pa_hl must be (time, level1, lat, lon)")
     nt, nl1, ny, nx = ph.shape
@@ -182,7 +185,7 @@ def integ_geopot(pa_hl, zgs, ta, hus, level1=None, p_ref=30000):
         pref_field = _dev(p_ref, dt).reshape(nt, ny, nx)
     out = torch.empty((nt, ny, nx), device=ph.device, dtype=torch.float64)
     err = _new_err()
-    fn = getattr(N.lib, "pgw_integ_geopot_" + _sfx(dt))
+    fn = getattr(N.lib, "pgw_integ_geopot_" + _sfx(dt) + ("_f32" if dts != dt else ""))
     for t in range(nt):
         N.check(fn(_p(ph[t]), _p(zd[t]), _p(td[t]), _p(qd[t]),
                    _p(pref_field[t]) if pref_field is not None else _p(None), pref_scalar,

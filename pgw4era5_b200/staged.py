@@ -154,7 +154,9 @@ def apply_staged(eng, era, era_step_dt, out=None, ignore_top_pressure_error=Fals
             p_ref_arg = float(settings.p_ref_inp)
         hus = F.relative_to_specific_humidity(vars_pgw["hur"], pa_pgw, vars_pgw["ta"])          # :262-266
         phi_pgw = F.integ_geopot(pa_hl_pgw, FIS, vars_pgw["ta"], hus, None, p_ref_arg)           # :269-276
-        phi_era = F.integ_geopot(pa_hl_era, FIS, T, QV, None, p_ref_arg)                         # :280-287
+        # the float32 T and QV of the file are handed over as they are: Rd * Tv in float32, like numpy (:144)
+        phi_era = F.integ_geopot(pa_hl_era, FIS, f["T"].reshape(1, L, ny, nx), f["QV"].reshape(1, L, ny, nx),
+                                 None, p_ref_arg)                                                 # :280-287
         ta_low = vars_pgw["ta"][0, L - 1].reshape(ncol).contiguous()
         maxerr.zero_()
         N.check(N.lib.pgw_ps_adjust_f64(_p(phi_pgw), _p(phi_era), _p(dphi_clim), _p(ps_pgw), _p(ta_low),

@@ -94,17 +94,29 @@ def test_integ_geopot_vs_oracle(F):
     era = S.to_numpy(S.make_era5(6, 20, 31))
     ak, bk = era["ak"], era["bk"]
     pa_hl = ak[None, :, None, None] + era["PS"].astype(np.float64)[:, None] * bk[None, :, None, None]
-    ref = O.integ_geopot(pa_hl, era["FIS"], era["T"], era["QV"], 30000.0)
-    out = F.integ_geopot(pa_hl, era["FIS"].astype(np.float64), era["T"].astype(np.float64),
-                         era["QV"].astype(np.float64), None, 30000.0)
-    np.testing.assert_allclose(out, ref, rtol=0, atol=1e-8)
+    fis, T64, Q64 = era["FIS"].astype(np.float64), era["T"].astype(np.float64), era["QV"].astype(np.float64)
     pref = np.where(era["PS"] > 90000, 50000.0, 30000.0)
-    np.testing.assert_allclose(F.integ_geopot(pa_hl, era["FIS"].astype(np.float64), era["T"].astype(np.float64),
-                                              era["QV"].astype(np.float64), None, pref),
-                               O.integ_geopot(pa_hl, era["FIS"], era["T"], era["QV"], pref), rtol=0, atol=1e-8)
+    for p_ref in (30000.0, pref):
+        # all float64, and float32 T/QV with float64 pressures (Rd * Tv in float32, like numpy in the reference)
+        np.testing.assert_allclose(F.integ_geopot(pa_hl, fis, T64, Q64, None, p_ref),
+                                   O.integ_geopot(pa_hl, fis, T64, Q64, p_ref), rtol=0, atol=1e-8)
+        np.testing.assert_allclose(F.integ_geopot(pa_hl, fis, era["T"], era["QV"], None, p_ref),
+                                   O.integ_geopot(pa_hl, fis, era["T"], era["QV"], p_ref), rtol=0, atol=1e-8)
+    d = np.abs(O.integ_geopot(pa_hl, fis, era["T"], era["QV"], 30000.0) - O.integ_geopot(pa_hl, fis, T64, Q64, 30000.0))
+    assert 1e-5 < d.max() < 2e-2                      # the two really differ
     with pytest.raises(ValueError, match="below the surface"):
-        F.integ_geopot(pa_hl, era["FIS"].astype(np.float64), era["T"].astype(np.float64),
-                       era["QV"].astype(np.float64), None, 120000.0)
+        F.integ_geopot(pa_hl, fis, T64, Q64, None, 120000.0)
+
+
+def test_integ_geopot_vs_executed_reference(F):
+    """functions.py:128-189 run unmodified over oracle/xrlite.py (tests/golden/reference_glue.npz)."""
+    import os
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_glue.npz"))
+    ak, bk, ps = G["ig_ak"], G["ig_bk"], G["ig_ps"]
+    pa_hl = ak[None, :, None, None] + ps[:, None] * bk[None, :, None, None]
+    for tag, p_ref in (("30000", 30000), ("50000", 50000.0), ("col", G["ig_pref_col"])):
+        out = F.integ_geopot(pa_hl, G["ig_zgs"], G["ig_ta"], G["ig_hus"], None, p_ref)
+        np.testing.assert_allclose(out, G["ig_phi_" + tag], rtol=0, atol=1e-8)
 
 
 def test_integrate_tos_golden(F, golden):
