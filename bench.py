@@ -199,6 +199,8 @@ def run_ours(a):
     from pgw4era5_b200 import parallel as P
 
     settings.i_debug = 0
+    if os.environ.get("PGW_BENCH_P_REF"):        # tuning experiments only (changes the workload; not a bench line)
+        settings.p_ref_inp = float(os.environ["PGW_BENCH_P_REF"])
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))

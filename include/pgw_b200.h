@@ -322,6 +322,13 @@ int pgw_regrid_bilinear_f32(const float *src, float *dst, const float *polemean,
 int pgw_smooth_harmonic_f32(const float *series, float *out, int nt, long long npoint,
                             void *stream);
 
+/* ------------------------------------------------------------------------
+ * File pipeline: byte order of n 32-bit words, in place (data 16-byte aligned).
+ * NetCDF-3 stores big-endian floats; replaces the decode/encode xarray performs on the CPU
+ * inside open_dataset / to_netcdf (step_03_apply_to_era.py:60, :378) for the float32 fields.
+ * ---------------------------------------------------------------------- */
+int pgw_byteswap32(void *data, long long n, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -341,6 +341,34 @@ int pgw_time_interp_f32(const float *lo, const float *hi, double x_hi, double x_
     return pgw_check_launch("time_interp_kernel");
 }
 
+// ---------------------------------------------------------------------------
+// NetCDF-3 stores big-endian numbers: the file pipeline moves the raw bytes of the float32 fields
+// between the file and pinned host memory and swaps them here, next to the H2D / D2H copies
+// (step_03_apply_to_era.py:60, :378 -- the decode xarray does on the CPU).  In place, 16 bytes/thread.
+// ---------------------------------------------------------------------------
+namespace pgw {
+__global__ void __launch_bounds__(256) byteswap32_kernel(uint32_t *__restrict__ data, long long n) {
+    const long long n4 = n >> 2;
+    uint4 *const v = reinterpret_cast<uint4 *>(data);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        uint4 x = v[i];
+        x.x = __byte_perm(x.x, 0, 0x0123); x.y = __byte_perm(x.y, 0, 0x0123);
+        x.z = __byte_perm(x.z, 0, 0x0123); x.w = __byte_perm(x.w, 0, 0x0123);
+        v[i] = x;
+    }
+    for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        data[i] = __byte_perm(data[i], 0, 0x0123);
+}
+}  // namespace pgw
+
+int pgw_byteswap32(void *data, long long n, void *stream) {
+    PGW_REQUIRE(data && n > 0 && (reinterpret_cast<uintptr_t>(data) & 15u) == 0);
+    pgw::byteswap32_kernel<<<ew_grid((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(
+        static_cast<uint32_t *>(data), n);
+    return pgw_check_launch("byteswap32_kernel");
+}
+
 int pgw_time_mean_f32(const float *series, int ntime, float *out, long long n, void *stream) {
     PGW_REQUIRE(series && out && ntime > 0 && n > 0);
     time_mean_kernel<<<ew_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(series, ntime, out, n);

@@ -5,7 +5,11 @@ with one CUDA stream each keep the PCIe link busy in both directions: while slot
 A's results travel device->host, slot B's inputs travel host->device and its
 kernel runs.  This is the path `bench.py` reports as ``e2e``.
 """
+import ctypes as C
+
 import torch
+
+from . import _native as N
 
 IN_FIELDS = ("PS", "FIS", "FR_LAND", "FR_SEA_ICE", "T_SKIN", "T_SO", "T", "QV", "U", "V")
 OUT_FIELDS = ("PS", "T_SKIN", "FR_SEA_ICE", "T_SO", "T", "QV", "U", "V", "delta_ps")
@@ -28,8 +32,14 @@ class HostPipeline:
             dout = torch.empty(self.n_out, device=dev, dtype=torch.float32)
             self.slots.append(dict(stream=torch.cuda.Stream(device=dev), din=din, dout=dout,
                                    vin=self._views(din, self.in_levels), vout=self._views(dout, self.out_levels),
-                                   pending=None, host_out=None))
+                                   pending=None, host_out=None, raw=False))
         self.count = 0
+
+    @staticmethod
+    def _swap(t):
+        """Byte order of a float32 device buffer, in place, on the current stream (NetCDF-3 is big-endian)."""
+        N.check(N.lib.pgw_byteswap32(C.c_void_p(t.data_ptr()), t.numel(),
+                                     C.c_void_p(torch.cuda.current_stream().cuda_stream)), "pgw_byteswap32")
 
     def _views(self, flat, levels):
         out, off = {}, 0
@@ -63,6 +73,8 @@ class HostPipeline:
             before = self.eng.stats["reruns"]
             res = p.result()
             if self.eng.stats["reruns"] != before:          # rerun wrote new device results
+                if slot["raw"]:
+                    self._swap(slot["dout"])
                 slot["host_out"]["flat"].copy_(slot["dout"], non_blocking=True)
             slot["stream"].synchronize()
         slot["pending"] = None
@@ -70,18 +82,24 @@ class HostPipeline:
         out["n_iter"] = res["n_iter"]
         return out
 
-    def run(self, host_in, era_step_dt, host_out, **kw):
+    def run(self, host_in, era_step_dt, host_out, raw=False, **kw):
         """Enqueue one timestep: H2D, fused pass, D2H.  Returns the finished result of the
-        timestep that previously used this slot (or None)."""
+        timestep that previously used this slot (or None).  ``raw``: the host buffers hold the
+        big-endian bytes of a NetCDF-3 file (nc3raw); they are swapped on the device after the
+        H2D copy and before the D2H copy."""
         slot = self.slots[self.count % self.nslots]
         sid = self.count % self.nslots
         self.count += 1
         done = self._finish(slot)
         with torch.cuda.stream(slot["stream"]):
             slot["din"].copy_(host_in["flat"], non_blocking=True)
+            if raw:
+                self._swap(slot["din"])
             slot["pending"] = self.eng.submit(slot["vin"], era_step_dt, out=slot["vout"], slot=sid, **kw)
+            if raw:
+                self._swap(slot["dout"])
             host_out["flat"].copy_(slot["dout"], non_blocking=True)
-            slot["host_out"] = host_out
+            slot["host_out"], slot["raw"] = host_out, raw
         return done
 
     def drain(self):

@@ -120,12 +120,75 @@ _ERA_NAMES = lambda vmap: dict(PS=vmap['ps'], FIS=vmap['zgs'], FR_LAND=vmap['sft
                                V=vmap['va'])
 
 
+_WRITTEN = ("PS", "T", "QV", "U", "V", "T_SKIN", "T_SO", "FR_SEA_ICE")
+IO_STATS = {"raw": 0, "decoded": 0}          # files per I/O path of pgw_for_era5_files (tests, bench_files.py)
+
+
+def _raw_layout(path, names, host_in):
+    """The header of ``path`` if the file can go through the pipeline without decoding: NetCDF-3, one
+    record at most, every ERA5 field float32 with the size of its host buffer, no RELHUM to drop
+    (step_03:371).  Else None (the decoding path is taken)."""
+    from .nc3raw import NC_FLOAT, NotNetCDF3, RawNC3
+    if os.environ.get("PGW_RAW_IO", "1") == "0":
+        return None
+    try:
+        raw = RawNC3(path)
+    except (NotNetCDF3, OSError):
+        return None
+    if raw.numrecs > 1 or settings.var_name_map['hur'] in raw.vars:
+        return None
+    for key, name in names.items():
+        v = raw.vars.get(name)
+        if v is None or v.nc_type != NC_FLOAT or (v.is_record and raw.numrecs != 1) or \
+                v.nbytes != host_in[key].numel() * 4:
+            return None
+    return raw
+
+
+def _copy_range(fd_in, fd_out, off, count):
+    """Bytes [off, off+count) of fd_in to the same place in fd_out, in the kernel where possible."""
+    while count > 0:
+        try:
+            n = os.copy_file_range(fd_in, fd_out, count, off, off)
+        except (OSError, AttributeError):
+            n = os.pwrite(fd_out, os.pread(fd_in, min(count, 1 << 24), off), off)
+        if n <= 0:
+            raise IOError("short copy")
+        off += n
+        count -= n
+
+
+def _write_raw(raw, names, inp_path, out_path, host_out):
+    """The output file = the input file with the eight updated fields replaced (step_03:367-378): the
+    bytes in between are copied file to file, the fields come straight from the (big-endian) host buffers."""
+    segs = sorted((raw.offset(names[k]), raw.vars[names[k]].nbytes, k) for k in _WRITTEN)
+    fd_in = os.open(inp_path, os.O_RDONLY)
+    fd_out = os.open(out_path, os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o644)
+    try:
+        size = os.fstat(fd_in).st_size
+        pos = 0
+        for off, nbytes, key in segs:
+            _copy_range(fd_in, fd_out, pos, off - pos)
+            mv = memoryview(host_out[key].numpy()).cast("B")
+            done = 0
+            while done < nbytes:
+                done += os.pwrite(fd_out, mv[done:nbytes], off + done)
+            pos = off + nbytes
+        _copy_range(fd_in, fd_out, pos, size - pos)
+    finally:
+        os.close(fd_in)
+        os.close(fd_out)
+
+
 def pgw_for_era5_files(steps, delta_input_dir, ignore_top_pressure_error, debug_mode=None):
     """
     The production mode of ``pgw_for_era5`` for a LIST of files on one GPU, as a three-stage
     pipeline: a reader thread decodes file i+1 into pinned host buffers and
     a writer thread stores file i-1 while the GPU works on file i (``hostpipe.HostPipeline``:
-    H2D, fused pass and D2H of consecutive files overlap on two CUDA streams).  Results are
+    H2D, fused pass and D2H of consecutive files overlap on two CUDA streams).  NetCDF-3 files with
+    float32 fields are not decoded at all: the reader moves the raw big-endian bytes of the fields into
+    pinned memory (``nc3raw``), the GPU swaps the byte order next to the copies (``pgw_byteswap32``) and
+    the writer assembles the output from the input file and the result buffers.  Results are
     identical to calling ``pgw_for_era5`` file by file.  ``steps``: dicts with inp_era_file_path,
     out_era_file_path, era_step_dt.  Returns the iteration counts.
     """
@@ -158,8 +221,18 @@ def pgw_for_era5_files(steps, delta_input_dir, ignore_top_pressure_error, debug_
             for k, st in enumerate(steps):
                 if settings.i_debug >= 0:
                     print('Start working on input file {}'.format(st["inp_era_file_path"]))
-                era_file = first if k == 0 else ncio.open_dataset(st["inp_era_file_path"], decode_cf=False)
                 h = free_in.get()
+                raw = _raw_layout(st["inp_era_file_path"], names, h)
+                if raw is not None and os.path.realpath(st["inp_era_file_path"]) != \
+                        os.path.realpath(st["out_era_file_path"]):
+                    with open(st["inp_era_file_path"], "rb", buffering=0) as f:
+                        for key in IN_FIELDS:
+                            raw.read_into(f, names[key], h[key].numpy())
+                    IO_STATS["raw"] += 1
+                    loaded.put((st, raw, h))
+                    continue
+                IO_STATS["decoded"] += 1
+                era_file = first if k == 0 else ncio.open_dataset(st["inp_era_file_path"], decode_cf=False)
                 for key in IN_FIELDS:
                     h[key].numpy()[...] = np.asarray(era_file[names[key]].data, dtype=np.float32).reshape(h[key].shape)
                 loaded.put((st, era_file, h))
@@ -175,7 +248,13 @@ def pgw_for_era5_files(steps, delta_input_dir, ignore_top_pressure_error, debug_
                 if item is None:
                     return
                 st, era_file, host = item
-                for key in ("PS", "T", "QV", "U", "V", "T_SKIN", "T_SO", "FR_SEA_ICE"):
+                if not isinstance(era_file, ncio.Dataset):           # raw layout
+                    _write_raw(era_file, names, st["inp_era_file_path"], st["out_era_file_path"], host)
+                    free_out.put(host)
+                    if settings.i_debug >= 1:
+                        print('Done. Saved to file {}.'.format(st["out_era_file_path"]))
+                    continue
+                for key in _WRITTEN:
                     ref = era_file[names[key]]
                     era_file[names[key]] = ncio.Variable(
                         ref.dims, host[key].numpy().reshape(ref.data.shape).astype(ref.data.dtype), ref.attrs)
@@ -206,8 +285,8 @@ def pgw_for_era5_files(steps, delta_input_dir, ignore_top_pressure_error, debug_
                 break
             st, era_file, h_in = item
             h_out = free_out.get()
-            done = pipe.run(h_in, st["era_step_dt"], h_out, ignore_top_pressure_error=ignore_top_pressure_error,
-                            file_name=st["inp_era_file_path"])
+            done = pipe.run(h_in, st["era_step_dt"], h_out, raw=not isinstance(era_file, ncio.Dataset),
+                            ignore_top_pressure_error=ignore_top_pressure_error, file_name=st["inp_era_file_path"])
             in_flight.append((st, era_file, h_in, h_out))
             if done is not None:
                 retire(done)

@@ -131,8 +131,17 @@ def test_step_03_cli_pipelines_several_files(tmp_path):
     old = settings.i_debug
     settings.i_debug = -1
     try:
+        S3.IO_STATS.update(raw=0, decoded=0)
         n_pipe = S3.main(["-i", str(inp), "-o", str(out), "-d", str(dd), "-f", "2006080200", "-l", "2006080300",
                           "-H", "6", "-t"])
+        assert S3.IO_STATS == dict(raw=5, decoded=0)        # NetCDF-3 float32 files: no decoding on the host
+        os.environ["PGW_RAW_IO"] = "0"
+        try:
+            n_dec = S3.main(["-i", str(inp), "-o", str(tmp_path / "out_dec"), "-d", str(dd), "-f", "2006080200",
+                             "-l", "2006080300", "-H", "6", "-t"])
+        finally:
+            del os.environ["PGW_RAW_IO"]
+        assert S3.IO_STATS == dict(raw=5, decoded=5) and n_dec == n_pipe
         n_one = [S3.pgw_for_era5(str(inp / settings.era5_file_name_base.format(w)),
                                  str(out1 / settings.era5_file_name_base.format(w)), str(dd), w, True)
                  for w in whens]
@@ -148,6 +157,14 @@ def test_step_03_cli_pipelines_several_files(tmp_path):
         # files take the rewrite path (k_spec > N), which recovers e from the fp32 QV: a few ulps
         np.testing.assert_allclose(a["QV"].data, b["QV"].data, rtol=0, atol=5e-9, err_msg=name)
         assert "RELHUM" not in a
+        # raw and decoding pipelines: the same bytes in every variable, attributes kept
+        c = ncio.open_dataset(str(tmp_path / "out_dec" / name))
+        for key in a.keys():
+            if key == "QV":          # k_spec of the second run starts from the first run's history (see above)
+                np.testing.assert_allclose(a[key].data, c[key].data, rtol=0, atol=5e-9, err_msg=name)
+            else:
+                np.testing.assert_array_equal(a[key].data, c[key].data, err_msg="%s %s" % (name, key))
+            assert a[key].attrs == c[key].attrs and a[key].dims == c[key].dims
 
 
 def test_step_01_cfday_interp_to_plev(tmp_path):

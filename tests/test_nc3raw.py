@@ -64,3 +64,51 @@ def test_rejects_other_files(tmp_path):
     p.write_bytes(b"\x89HDF\r\n\x1a\n" + b"\0" * 64)
     with pytest.raises(NotNetCDF3):
         RawNC3(str(p))
+
+
+def test_write_raw_assembles_the_output_file(tmp_path):
+    """step_03's raw writer: input file bytes + the updated fields from big-endian host buffers."""
+    import torch
+    from pgw4era5_b200 import settings, step_03_apply_to_era as S3
+    rng = np.random.default_rng(9)
+    nl, ny, nx, ns = 3, 4, 5, 2
+    ds = ncio.Dataset()
+    ds["time"] = ncio.Variable(("time",), np.array([6.0]), {"units": "hours since 2006-08-01 00:00:00"})
+    ds["lat"] = ncio.Variable(("lat",), np.arange(ny, dtype=float)); ds["lon"] = ncio.Variable(("lon",), np.arange(nx, dtype=float))
+    ds["level"] = ncio.Variable(("level",), np.arange(1.0, nl + 1)); ds["soil1"] = ncio.Variable(("soil1",), np.arange(1.0, ns + 1))
+    ds["ak"] = ncio.Variable(("level",), rng.normal(size=nl))
+    shapes = dict(PS=(1, ny, nx), FIS=(1, ny, nx), FR_LAND=(1, ny, nx), FR_SEA_ICE=(1, ny, nx), T_SKIN=(1, ny, nx),
+                  T_SO=(1, ns, ny, nx), T=(1, nl, ny, nx), QV=(1, nl, ny, nx), U=(1, nl, ny, nx), V=(1, nl, ny, nx))
+    dims = {3: ("time", "lat", "lon"), 4: ("time", "level", "lat", "lon")}
+    for k, shp in shapes.items():
+        d = ("time", "soil1", "lat", "lon") if k == "T_SO" else dims[len(shp)]
+        ds[k] = ncio.Variable(d, rng.normal(size=shp).astype(np.float32), {"long_name": k})
+    inp, out = str(tmp_path / "in.nc"), str(tmp_path / "out.nc")
+    ds.to_netcdf(inp)
+    names = S3._ERA_NAMES(settings.var_name_map)
+    host_in = {k: torch.empty(shp, dtype=torch.float32) for k, shp in shapes.items()}
+    raw = S3._raw_layout(inp, names, host_in)
+    assert raw is not None
+    with open(inp, "rb", buffering=0) as f:
+        for k in shapes:
+            raw.read_into(f, names[k], host_in[k].numpy())
+    for k in shapes:          # the raw bytes are the big-endian values
+        np.testing.assert_array_equal(host_in[k].numpy().view(">f4").astype(np.float32), ds[k].data)
+    new = {k: rng.normal(size=shapes[k]).astype(np.float32) for k in S3._WRITTEN}
+    host_out = {k: torch.from_numpy(v.astype(">f4").view(np.float32)) for k, v in new.items()}
+    S3._write_raw(raw, names, inp, out, host_out)
+    assert os.path.getsize(out) == os.path.getsize(inp)
+    back = ncio.open_dataset(out)
+    for k in shapes:
+        np.testing.assert_array_equal(back[k].data, new[k] if k in new else ds[k].data)
+        assert back[k].attrs["long_name"] == k
+    np.testing.assert_array_equal(back["ak"].data, ds["ak"].data)
+    # files the raw path must leave to the decoding path: float64 fields, RELHUM present
+    ds2 = ds.copy()
+    ds2["PS"] = ncio.Variable(("time", "lat", "lon"), ds["PS"].data.astype(np.float64))
+    ds2.to_netcdf(str(tmp_path / "f64.nc"))
+    assert S3._raw_layout(str(tmp_path / "f64.nc"), names, host_in) is None
+    ds3 = ds.copy()
+    ds3["RELHUM"] = ncio.Variable(("time", "level", "lat", "lon"), ds["T"].data)
+    ds3.to_netcdf(str(tmp_path / "rh.nc"))
+    assert S3._raw_layout(str(tmp_path / "rh.nc"), names, host_in) is None

@@ -190,3 +190,17 @@ def test_regrid_identity_and_pole_rows(F):
     poles = F.regrid_arrays(data, lat, lon, np.array([-90.0, 90.0]), lon)
     np.testing.assert_allclose(poles[:, 0], np.repeat(data[:, 0].mean(-1, keepdims=True), len(lon), -1), atol=1e-6)
     np.testing.assert_allclose(poles[:, 1], np.repeat(data[:, -1].mean(-1, keepdims=True), len(lon), -1), atol=1e-6)
+
+
+def test_byteswap32():
+    """pgw_byteswap32: the big-endian float32 words of a NetCDF-3 file, swapped in place on the device."""
+    import ctypes as C
+    import torch
+    from pgw4era5_b200 import _native as N
+    rng = np.random.default_rng(11)
+    for n in (1, 3, 4, 1023, 4096 + 5):
+        x = rng.normal(size=n).astype(np.float32)
+        d = torch.from_numpy(x.astype(">f4").view(np.float32).copy()).cuda()
+        N.check(N.lib.pgw_byteswap32(C.c_void_p(d.data_ptr()), n, C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+                "pgw_byteswap32")
+        np.testing.assert_array_equal(d.cpu().numpy(), x)
