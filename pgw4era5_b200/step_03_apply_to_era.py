@@ -158,23 +158,35 @@ def _copy_range(fd_in, fd_out, off, count):
         count -= n
 
 
-def _write_raw(raw, names, inp_path, out_path, host_out):
+def _write_raw(raw, names, inp_path, out_path, host_out, pool=None):
     """The output file = the input file with the eight updated fields replaced (step_03:367-378): the
-    bytes in between are copied file to file, the fields come straight from the (big-endian) host buffers."""
+    bytes in between are copied file to file, the fields come straight from the (big-endian) host buffers.
+    All writes are positional, so ``pool`` (a ThreadPoolExecutor) may run them side by side."""
     segs = sorted((raw.offset(names[k]), raw.vars[names[k]].nbytes, k) for k in _WRITTEN)
     fd_in = os.open(inp_path, os.O_RDONLY)
     fd_out = os.open(out_path, os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o644)
+
+    def put(off, nbytes, key):
+        mv = memoryview(host_out[key].numpy()).cast("B")
+        done = 0
+        while done < nbytes:
+            done += os.pwrite(fd_out, mv[done:nbytes], off + done)
+
     try:
         size = os.fstat(fd_in).st_size
-        pos = 0
+        os.ftruncate(fd_out, size)
+        jobs, pos = [], 0
         for off, nbytes, key in segs:
-            _copy_range(fd_in, fd_out, pos, off - pos)
-            mv = memoryview(host_out[key].numpy()).cast("B")
-            done = 0
-            while done < nbytes:
-                done += os.pwrite(fd_out, mv[done:nbytes], off + done)
+            jobs.append((_copy_range, (fd_in, fd_out, pos, off - pos)))
+            jobs.append((put, (off, nbytes, key)))
             pos = off + nbytes
-        _copy_range(fd_in, fd_out, pos, size - pos)
+        jobs.append((_copy_range, (fd_in, fd_out, pos, size - pos)))
+        if pool is None:
+            for fn, args in jobs:
+                fn(*args)
+        else:
+            for fut in [pool.submit(fn, *args) for fn, args in jobs]:
+                fut.result()
     finally:
         os.close(fd_in)
         os.close(fd_out)
@@ -194,6 +206,7 @@ def pgw_for_era5_files(steps, delta_input_dir, ignore_top_pressure_error, debug_
     """
     import queue
     import threading
+    from concurrent.futures import ThreadPoolExecutor
     from .hostpipe import HostPipeline, IN_FIELDS
     if not steps:
         return []
@@ -215,6 +228,10 @@ def pgw_for_era5_files(steps, delta_input_dir, ignore_top_pressure_error, debug_
         free_out.put(pipe.alloc_host_outputs())
     loaded, to_write = queue.Queue(maxsize=n_in_buf), queue.Queue()
     failure = []
+    # the raw path is a copy between the page cache and pinned memory: a few threads per direction
+    # (pread / pwrite release the GIL) move the fields of one file side by side
+    n_io = max(1, min(4, (os.cpu_count() or 2) // 2))
+    rpool, wpool = ThreadPoolExecutor(n_io), ThreadPoolExecutor(n_io)
 
     def reader():
         try:
@@ -226,8 +243,8 @@ def pgw_for_era5_files(steps, delta_input_dir, ignore_top_pressure_error, debug_
                 if raw is not None and os.path.realpath(st["inp_era_file_path"]) != \
                         os.path.realpath(st["out_era_file_path"]):
                     with open(st["inp_era_file_path"], "rb", buffering=0) as f:
-                        for key in IN_FIELDS:
-                            raw.read_into(f, names[key], h[key].numpy())
+                        for fut in [rpool.submit(raw.read_into, f, names[key], h[key].numpy()) for key in IN_FIELDS]:
+                            fut.result()
                     IO_STATS["raw"] += 1
                     loaded.put((st, raw, h))
                     continue
@@ -249,7 +266,7 @@ def pgw_for_era5_files(steps, delta_input_dir, ignore_top_pressure_error, debug_
                     return
                 st, era_file, host = item
                 if not isinstance(era_file, ncio.Dataset):           # raw layout
-                    _write_raw(era_file, names, st["inp_era_file_path"], st["out_era_file_path"], host)
+                    _write_raw(era_file, names, st["inp_era_file_path"], st["out_era_file_path"], host, wpool)
                     free_out.put(host)
                     if settings.i_debug >= 1:
                         print('Done. Saved to file {}.'.format(st["out_era_file_path"]))
@@ -296,6 +313,8 @@ def pgw_for_era5_files(steps, delta_input_dir, ignore_top_pressure_error, debug_
     finally:
         to_write.put(None)
         tw.join()
+        rpool.shutdown(wait=False)
+        wpool.shutdown(wait=False)
     if failure:
         raise failure[0]
     return n_iters

@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--dir", default="/tmp/pgw_files")
     ap.add_argument("--ny", type=int, default=201)
     ap.add_argument("--nx", type=int, default=281)
+    ap.add_argument("--raw-only", action="store_true", help="skip the decoding pipeline and the file-by-file run")
     a = ap.parse_args()
     import torch
     from pgw4era5_b200 import settings, synthetic as S, step_03_apply_to_era as S3
@@ -55,6 +56,13 @@ def main():
     S3.main(argv("pipe"))
     t_pipe = time.perf_counter() - t
     raw_files = S3.IO_STATS["raw"]
+    if a.raw_only:
+        print(json.dumps({"workload": "%d ERA5 files %dx%dx137 (%.0f MB each), NetCDF-3 in -> NetCDF-3 out" %
+                                      (a.files, a.ny, a.nx, fbytes / 1e6),
+                          "pipelined_files_per_s": a.files / t_pipe, "raw_io_files": raw_files,
+                          "pipelined_MBps_in_plus_out": 2 * fbytes * a.files / t_pipe / 1e6}))
+        shutil.rmtree(a.dir, ignore_errors=True)
+        return
     os.environ["PGW_RAW_IO"] = "0"             # the same pipeline with the NetCDF codec on the host (scipy)
     t = time.perf_counter()
     S3.main(argv("pipe_dec"))
