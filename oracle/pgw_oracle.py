@@ -7,21 +7,22 @@ and the ``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import
 it.  Nothing under ``pgw4era5_b200/`` imports it; the product path fails loudly
 when the CUDA library is missing.
 
-Pinning status (see DESIGN.md "Oracle"):
-  * pinned against the reference's own code run in the build container
-    (``oracle/make_golden.py`` imports ``/root/reference/functions.py`` with
-    xarray/pyvista/pyproj stubbed and stores outputs in ``tests/golden/``):
-    interp_extrap_1d, interp_1d_for_timelatlon, replace_delta_sfc,
-    determine_p_ref, integrate_tos, harmonic_ac_analysis, the three pure
-    humidity helpers, saturation_vapor_pressure_water_or_ice, dt64_to_dt.
-  * pinned against scipy's interp1d (the third-party arithmetic behind
-    xarray ``.interp``; environment.yml pins scipy 1.9.3, xarray 2022.12.0):
-    time interpolation and the two 1-D passes of regrid_lat_lon.
-  * PARITY UNPINNED by the reference's own tests (it has none) for the
-    xarray glue restated here: integ_geopot, load_delta's calendar logic,
-    vert_interp_delta, regrid_lat_lon, filter_data and the orchestration of
-    pgw_for_era5.  These follow the reference line by line; each function
-    cites the file:line it restates.
+Pinning status.  The reference has no tests and ships no data, and it
+needs xarray, which the build container lacks; the oracle is pinned by EXECUTING the reference in
+the build container and committing what it returns:
+  * ``oracle/make_golden.py`` -> tests/golden/reference_functions.npz: the numpy/numba functions of
+    /root/reference/functions.py imported unmodified (xarray/pyvista/pyproj stubbed): interp_extrap_1d,
+    interp_1d_for_timelatlon, replace_delta_sfc, determine_p_ref, integrate_tos,
+    harmonic_ac_analysis, the humidity helpers, dt64_to_dt.  Bit-exact (tests/test_oracle_golden.py).
+  * ``oracle/make_golden_glue.py`` -> tests/golden/reference_glue.npz: the xarray-bound functions
+    (integ_geopot, load_delta, load_delta_interp, vert_interp_delta, interp_logp_4d, regrid_lat_lon,
+    filter_data, the alpha-blended saturation pressure) and the WHOLE of step_03's pgw_for_era5
+    (six settings), run unmodified over ``oracle/xrlite.py``, a restatement of the xarray semantics
+    they use.  tests/test_oracle_glue_golden.py: identical iteration counts and per-iteration max
+    errors, PS to 2e-10 Pa, functions to float64 round-off.
+  * scipy's interp1d (the arithmetic behind xarray ``.interp``): tests/test_oracle_properties.py.
+  * PARITY UNPINNED for xarray itself only: xrlite restates its documented behaviour.
+Each function cites the file:line it restates.
 
 All arrays are numpy, C-order, dims ``(time, level, lat, lon)``.
 """
