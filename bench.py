@@ -280,16 +280,17 @@ def run_ours(a):
     e2e = None
     if a.e2e_steps > 0:
         from pgw4era5_b200.hostpipe import HostPipeline
-        pipe = HostPipeline(eng, ny, nx)
-        hin = [pipe.pin_inputs(ring[i % a.ring]) for i in range(2)]
-        houts = [pipe.alloc_host_outputs() for _ in range(2)]
-        for i in range(2):
-            pipe.run(hin[i % 2], when(i), houts[i % 2], ignore_top_pressure_error=True)
+        ns = a.e2e_slots
+        pipe = HostPipeline(eng, ny, nx, nslots=ns)
+        hin = [pipe.pin_inputs(ring[i % a.ring]) for i in range(ns)]
+        houts = [pipe.alloc_host_outputs() for _ in range(ns)]
+        for i in range(ns):
+            pipe.run(hin[i % ns], when(i), houts[i % ns], ignore_top_pressure_error=True)
         pipe.drain()
         barrier()
         t0 = time.perf_counter()
         for i in range(a.e2e_steps):
-            pipe.run(hin[i % 2], when(i), houts[i % 2], ignore_top_pressure_error=True)
+            pipe.run(hin[i % ns], when(i), houts[i % ns], ignore_top_pressure_error=True)
         pipe.drain()
         torch.cuda.synchronize()
         el = time.perf_counter() - t0
@@ -298,7 +299,7 @@ def run_ours(a):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e = {"value": world * a.e2e_steps / float(t.item()), "unit": "timesteps/s",
                "h2d_bytes_per_step": pipe.h2d_bytes, "d2h_bytes_per_step": pipe.d2h_bytes,
-               "steps": a.e2e_steps}
+               "steps": a.e2e_steps, "slots": ns}
 
     # ---- roofline of the dominant kernel (the fused column kernel)
     peak, peak_kind = measured_peak_gbs()
@@ -359,6 +360,7 @@ def main():
     ap.add_argument("--grid", default="GL", choices=sorted(GRIDS))
     ap.add_argument("--ring", type=int, default=4)
     ap.add_argument("--e2e-steps", type=int, default=24)
+    ap.add_argument("--e2e-slots", type=int, default=2, help="timesteps in flight in the host-buffer pipeline")
     ap.add_argument("--no-cpu", action="store_true")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup

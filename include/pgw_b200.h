@@ -323,6 +323,24 @@ int pgw_smooth_harmonic_f32(const float *series, float *out, int nt, long long n
                             void *stream);
 
 /* ------------------------------------------------------------------------
+ * step_02, ocean variables (tos, siconc): NaN-ignoring Gaussian-kernel regridding from the curvilinear
+ * GCM ocean grid.  Replaces nan_ignoring_interp(), functions.py:900-1060.
+ * pgw_geod_to_meter_f64: the coordinate mapping of :946-973 / :1006-1022 -- lon > 180 -> lon - 360,
+ *   lat_m = sign(lat) * geod.inv(lon, 0, lon, lat), lon_m = sign(lon) * geod.inv(0, lat, lon, lat),
+ *   half_turn (optional) = geod.inv(0, lat, 180, lat); WGS84 geodesics (pyproj Geod.inv in the reference).
+ * pgw_gauss_interp_f64: pyvista PolyData.interpolate(points, null_value=nan, radius, sharpness) of :1038-1048
+ *   (vtkPointInterpolator + vtkGaussianKernel) plus the land mask FR_LAND > 0.7 -> NaN (:1031, :1055):
+ *   src_lat_m ASCENDING [nsrc], src_lon_m [nsrc], src_val [nfield <= 12, nsrc] (NaN = absent for that
+ *   field), dst_* [ndst], land_fr [ndst] or NULL, out [nfield, ndst].
+ * ---------------------------------------------------------------------- */
+int pgw_geod_to_meter_f64(const double *lat_deg, const double *lon_deg, double *lat_m, double *lon_m,
+                          double *half_turn, long long n, void *stream);
+int pgw_gauss_interp_f64(const double *src_lat_m, const double *src_lon_m, const double *src_val,
+                         long long nsrc, int nfield, const double *dst_lat_m, const double *dst_lon_m,
+                         const float *land_fr, double *out, long long ndst, double radius, double sharpness,
+                         void *stream);
+
+/* ------------------------------------------------------------------------
  * File pipeline: byte order of n 32-bit words, in place (data 16-byte aligned).
  * NetCDF-3 stores big-endian floats; replaces the decode/encode xarray performs on the CPU
  * inside open_dataset / to_netcdf (step_03_apply_to_era.py:60, :378) for the float32 fields.

@@ -540,6 +540,147 @@ def regrid_lat_lon(data, lat_gcm, lon_gcm, targ_lat, targ_lon):
 
 
 # ---------------------------------------------------------------------------
+# NaN-ignoring Gaussian-kernel regridding of tos / siconc (functions.py:900-1060)
+#
+# PARITY UNPINNED: the arithmetic lives in two third-party packages that are neither vendored in
+# /root/reference nor installed here -- pyproj 3.4.0 (``Geod(ellps="WGS84").inv``, PROJ's geodesic.c
+# after Karney 2013) and pyvista 0.37.0 / vtk 9.2.2 (``PolyData.interpolate`` = vtkPointInterpolator
+# with a vtkGaussianKernel on a radius footprint, null-points strategy NULL_VALUE).  Their published
+# algorithms are restated: geodesic distances from the exact integrals of Karney (2013), eqs 7-8,
+# evaluated by Gauss-Legendre quadrature (the three distances the reference asks for are a meridian
+# arc, a geodesic between two points of EQUAL latitude and the distance to the point 180 degrees
+# away, which runs over the pole); the kernel as in vtkGaussianKernel::ComputeWeights:
+# w_i = exp(-(sharpness/radius)^2 d_i^2) over the points with d_i <= radius, normalised; an exact hit
+# (d^2 < 256 eps) takes that point's value; no point in the radius -> null value.
+# ---------------------------------------------------------------------------
+WGS84_A = 6378137.0
+WGS84_F = 1.0 / 298.257223563
+_GLX, _GLW = np.polynomial.legendre.leggauss(32)
+
+
+def _quad(f, lo, hi):
+    """Gauss-Legendre integral of f over [lo, hi] (arrays broadcast against the node axis)."""
+    lo, hi = np.asarray(lo, dtype=np.float64), np.asarray(hi, dtype=np.float64)
+    mid, half = 0.5 * (hi + lo), 0.5 * (hi - lo)
+    return half * np.sum(_GLW * f(mid[..., None] + half[..., None] * _GLX), axis=-1)
+
+
+def wgs84_meridian_arc(lat_deg):
+    """Distance along the meridian from the equator to |lat| [m]: Karney (2013) eq. 7 with alpha0 = 0
+    (sigma = reduced latitude, k = e'), i.e. what ``geod.inv(lon, 0, lon, lat)`` returns."""
+    f = WGS84_F
+    b = WGS84_A * (1 - f)
+    ep2 = f * (2 - f) / (1 - f) ** 2
+    beta = np.arctan((1 - f) * np.tan(np.radians(np.abs(np.asarray(lat_deg, dtype=np.float64)))))
+    return b * _quad(lambda s: np.sqrt(1 + ep2 * np.sin(s) ** 2), np.zeros_like(beta), beta)
+
+
+def wgs84_same_lat_distance(lat_deg, dlon_deg):
+    """Geodesic distance [m] between (lat, 0) and (lat, dlon), 0 <= dlon <= 180, i.e. what
+    ``geod.inv(0, lat, lon, lat)`` returns.  By symmetry the vertex of the geodesic lies half way;
+    the azimuth alpha0 at the equator crossing is found by bisection on the longitude integral
+    (Karney 2013, eq. 8), the distance follows from eq. 7."""
+    f = WGS84_F
+    b = WGS84_A * (1 - f)
+    ep2 = f * (2 - f) / (1 - f) ** 2
+    lat = np.abs(np.asarray(lat_deg, dtype=np.float64))
+    lat, dlon = np.broadcast_arrays(lat, np.abs(np.asarray(dlon_deg, dtype=np.float64)))
+    beta = np.arctan((1 - f) * np.tan(np.radians(lat)))
+    half = 0.5 * np.radians(dlon)
+    sb = np.sin(beta)
+
+    def half_dlon_and_dist(a0):
+        ca, sa = np.cos(a0), np.sin(a0)
+        k2 = ep2 * ca * ca
+        sig1 = np.arcsin(np.clip(sb / ca, -1.0, 1.0))
+        omega1 = np.arctan2(sa * np.sin(sig1), np.cos(sig1))
+        J = _quad(lambda s: (2 - f) / (1 + (1 - f) * np.sqrt(1 + k2[..., None] * np.sin(s) ** 2)),
+                  sig1, np.full_like(sig1, 0.5 * np.pi))
+        I1 = _quad(lambda s: np.sqrt(1 + k2[..., None] * np.sin(s) ** 2), sig1, np.full_like(sig1, 0.5 * np.pi))
+        return (0.5 * np.pi - omega1) - f * sa * J, 2.0 * b * I1
+
+    lo = np.zeros_like(beta)
+    hi = 0.5 * np.pi - beta                      # the point itself is the vertex: dlon = 0
+    for _ in range(100):
+        mid = 0.5 * (lo + hi)
+        h, _ = half_dlon_and_dist(mid)
+        big = h > half                           # half-longitude decreases with alpha0
+        lo = np.where(big, mid, lo)
+        hi = np.where(big, hi, mid)
+    _, dist = half_dlon_and_dist(0.5 * (lo + hi))
+    # on the equator the geodesic stays on the equator up to dlon = (1 - f) 180 degrees
+    equatorial = (beta == 0) & (half <= (1 - f) * 0.5 * np.pi)
+    dist = np.where(equatorial, WGS84_A * 2.0 * half, dist)
+    return np.where(dlon == 0, 0.0, dist)
+
+
+def wgs84_half_turn_distance(lat_deg):
+    """``geod.inv(0, lat, 180, lat)``: the geodesic to the point 180 degrees away runs over the pole."""
+    return 2.0 * (wgs84_meridian_arc(90.0) - wgs84_meridian_arc(lat_deg))
+
+
+def lonlat_to_meter(lon_deg, lat_deg):
+    """functions.py:958-973 / :1011-1022: (lat, lon) in degrees -> signed 'meter' coordinates."""
+    lon = np.asarray(lon_deg, dtype=np.float64)
+    lat = np.asarray(lat_deg, dtype=np.float64)
+    lat_m = wgs84_meridian_arc(lat) * np.sign(lat)
+    lon_m = wgs84_same_lat_distance(lat, lon) * np.sign(lon)
+    return lat_m, lon_m
+
+
+def gaussian_kernel_interp(src_xy, src_val, dst_xy, radius, sharpness, null_value=np.nan, chunk=2048):
+    """vtkPointInterpolator + vtkGaussianKernel (radius footprint, NULL_VALUE strategy), see above."""
+    src_xy, dst_xy = np.asarray(src_xy, dtype=np.float64), np.asarray(dst_xy, dtype=np.float64)
+    src_val = np.asarray(src_val, dtype=np.float64)
+    f2 = (sharpness / radius) ** 2
+    out = np.full(len(dst_xy), null_value, dtype=np.float64)
+    eps = np.finfo(np.float64).eps * 256.0
+    for i0 in range(0, len(dst_xy), chunk):
+        d = dst_xy[i0:i0 + chunk]
+        d2 = (d[:, None, 0] - src_xy[None, :, 0]) ** 2 + (d[:, None, 1] - src_xy[None, :, 1]) ** 2
+        inside = d2 <= radius * radius
+        w = np.where(inside, np.exp(-f2 * d2), 0.0)
+        sw = w.sum(axis=1)
+        val = (w * src_val[None, :]).sum(axis=1)
+        res = np.where(sw > 0, val / np.where(sw > 0, sw, 1.0), null_value)
+        hit = inside & (d2 < eps)
+        anyhit = hit.any(axis=1)
+        res[anyhit] = src_val[hit.argmax(axis=1)[anyhit]]
+        res[~inside.any(axis=1)] = null_value
+        out[i0:i0 + chunk] = res
+    return out
+
+
+def nan_ignoring_interp(land_fr, era5_lat, era5_lon, delta, gcm_lat2d, gcm_lon2d, kernel_radius, sharpness):
+    """functions.py:900-1060 for one 2-D field ``delta`` on a curvilinear grid (2-D lat/lon arrays).
+    Returns [len(era5_lat), len(era5_lon)] float64."""
+    gcm_lat_raw = np.asarray(gcm_lat2d, dtype=np.float64).reshape(-1).copy()
+    gcm_lon_raw = np.asarray(gcm_lon2d, dtype=np.float64).reshape(-1).copy()
+    gcm_val_raw = np.asarray(delta, dtype=np.float64).reshape(-1)
+    gcm_lon_raw[gcm_lon_raw > 180] -= 360                    # :946-948
+    ok = ~np.isnan(gcm_val_raw)                              # :951-954
+    gcm_val, gcm_lon, gcm_lat = gcm_val_raw[ok], gcm_lon_raw[ok], gcm_lat_raw[ok]
+    lat_m, lon_m = lonlat_to_meter(gcm_lon, gcm_lat)         # :958-973
+    off = wgs84_half_turn_distance(gcm_lat)
+    n = len(gcm_val)
+    val_bd = np.tile(gcm_val, 3)                             # :978-988
+    lat_bd = np.tile(lat_m, 3)
+    lon_bd = np.tile(lon_m, 3)
+    lon_bd[:n] -= off * 2
+    lon_bd[2 * n:] += off * 2
+    era5_lat = np.asarray(era5_lat, dtype=np.float64)
+    era5_lon = np.asarray(era5_lon, dtype=np.float64).copy()
+    era5_lon[era5_lon > 180] -= 360                          # :1006-1008
+    lat_f = np.repeat(era5_lat, len(era5_lon))               # :1011-1012
+    lon_f = np.tile(era5_lon, len(era5_lat))
+    e_lat_m, e_lon_m = lonlat_to_meter(lon_f, lat_f)
+    res = gaussian_kernel_interp(np.stack([lat_bd, lon_bd], axis=1), val_bd,
+                                 np.stack([e_lat_m, e_lon_m], axis=1), kernel_radius, sharpness)
+    res[np.asarray(land_fr, dtype=np.float64).reshape(-1) > 0.7] = np.nan      # :1031, :1055
+    return res.reshape(len(era5_lat), len(era5_lon))
+
+
+# ---------------------------------------------------------------------------
 # the per-timestep routine (step_03_apply_to_era.py:44-381)
 # ---------------------------------------------------------------------------
 def pgw_for_era5(era, deltas, era_step_dt, *, p_ref_inp=30000, adj_factor=0.95,

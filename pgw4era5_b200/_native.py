@@ -87,6 +87,8 @@ def _load():
         "pgw_integrate_tos_f64": (i, [vp, vp, vp, vp, vp, ll, vp]),
         "pgw_time_interp_f32": (i, [vp, vp, d, d, vp, ll, vp]),
         "pgw_byteswap32": (i, [vp, ll, vp]),
+        "pgw_geod_to_meter_f64": (i, [vp, vp, vp, vp, vp, ll, vp]),
+        "pgw_gauss_interp_f64": (i, [vp, vp, vp, ll, i, vp, vp, vp, vp, ll, d, d, vp]),
         "pgw_time_mean_f32": (i, [vp, i, vp, ll, vp]),
         "pgw_timestep_smem_bytes": (ll, [C.POINTER(TimestepArgs)]),
         "pgw_timestep_uses_tma": (i, [C.POINTER(TimestepArgs)]),

@@ -555,12 +555,91 @@ def regrid_lat_lon(ds_gcm, ds_era5, var_name, method='bilinear', i_use_xesmf=0):
     return out
 
 
+def lonlat_to_meter(lon_deg, lat_deg, half_turn=False):
+    """The coordinate mapping of nan_ignoring_interp (functions.py:946-973, :1006-1022) on the device:
+    longitudes above 180 are shifted by -360, then ``lat_m = sign(lat) * geod.inv(lon, 0, lon, lat)`` and
+    ``lon_m = sign(lon) * geod.inv(0, lat, lon, lat)`` on WGS84 (+ ``geod.inv(0, lat, 180, lat)``).
+    Returns float64 device tensors."""
+    lat = _dev(lat_deg, torch.float64).reshape(-1)
+    lon = _dev(lon_deg, torch.float64).reshape(-1)
+    lat_m, lon_m = torch.empty_like(lat), torch.empty_like(lat)
+    ht = torch.empty_like(lat) if half_turn else None
+    N.check(N.lib.pgw_geod_to_meter_f64(_p(lat), _p(lon), _p(lat_m), _p(lon_m), _p(ht), lat.numel(), _stream()),
+            "pgw_geod_to_meter_f64")
+    return (lat_m, lon_m, ht) if half_turn else (lat_m, lon_m)
+
+
+def nan_ignoring_interp_arrays(land_fr, era5_lat, era5_lon, values, gcm_lat2d, gcm_lon2d, kernel_radius, sharpness):
+    """
+    nan_ignoring_interp (functions.py:900-1060) on arrays, for any number of fields (months) at once:
+    ``values`` [nt, nj, ni] (or [nj, ni]) on the curvilinear ocean grid ``gcm_lat2d/gcm_lon2d`` [nj, ni]
+    -> float64 [nt, len(era5_lat), len(era5_lon)].  NaN source points are ignored per field, targets with
+    ``land_fr > 0.7`` and targets without a source point inside ``kernel_radius`` become NaN.
+    """
+    vals = _dev(values, torch.float64)
+    single = vals.dim() == 2
+    vals = vals.reshape(-1, vals.shape[-2] * vals.shape[-1])
+    nt, npts = vals.shape
+    glat = _dev(gcm_lat2d, torch.float64).reshape(-1)
+    glon = _dev(gcm_lon2d, torch.float64).reshape(-1)
+    if glat.numel() != npts or glon.numel() != npts:
+        raise ValueError("latitude/longitude of the ocean grid must be 2-D like the data")   # see :940-943
+    keep = ~torch.isnan(vals).all(dim=0)                   # points that are NaN in every field never count
+    glat, glon, vals = glat[keep], glon[keep], vals[:, keep]
+    lat_m, lon_m, off = lonlat_to_meter(glon, glat, half_turn=True)
+    # boundary points: the whole cloud once more to the west and to the east (:978-988)
+    lat_bd = torch.cat([lat_m, lat_m, lat_m])
+    lon_bd = torch.cat([lon_m - 2.0 * off, lon_m, lon_m + 2.0 * off])
+    lat_bd, order = torch.sort(lat_bd)
+    lon_bd = lon_bd[order].contiguous()
+    n = lat_m.numel()
+    era5_lat = np.asarray(_raw(era5_lat), dtype=np.float64).reshape(-1)
+    era5_lon = np.asarray(_raw(era5_lon), dtype=np.float64).reshape(-1)
+    ny, nx = len(era5_lat), len(era5_lon)
+    e_lat_m, e_lon_m = lonlat_to_meter(np.tile(era5_lon, ny), np.repeat(era5_lat, nx))     # :1011-1022
+    land = _dev(land_fr, torch.float32).reshape(-1).contiguous()
+    if land.numel() != ny * nx:
+        raise ValueError("land fraction must be on the ERA5 grid")
+    out = torch.empty((nt, ny * nx), device=vals.device, dtype=torch.float64)
+    for f0 in range(0, nt, 12):
+        f1 = min(nt, f0 + 12)
+        v3 = vals[f0:f1].repeat(1, 3)[:, order].contiguous()
+        o = torch.empty((f1 - f0, ny * nx), device=vals.device, dtype=torch.float64)
+        N.check(N.lib.pgw_gauss_interp_f64(_p(lat_bd), _p(lon_bd), _p(v3), 3 * n, f1 - f0, _p(e_lat_m), _p(e_lon_m),
+                                           _p(land), _p(o), ny * nx, float(kernel_radius), float(sharpness),
+                                           _stream()), "pgw_gauss_interp_f64")
+        out[f0:f1] = o
+    out = out.reshape(nt, ny, nx)
+    return _back(out[0] if single else out, values)
+
+
+def nan_ignoring_interp(da_era5_land_fr, da_delta, kernel_radius, sharpness):
+    """functions.py:900-1060 with the reference's signature, for array-likes that carry coordinates the
+    way xarray DataArrays do (``.values`` and ``.coords[name].values``)."""
+    return nan_ignoring_interp_arrays(
+        da_era5_land_fr.values, da_era5_land_fr.coords[LAT_ERA].values, da_era5_land_fr.coords[LON_ERA].values,
+        da_delta.values, da_delta.coords[LAT_GCM_OCEAN].values, da_delta.coords[LON_GCM_OCEAN].values,
+        kernel_radius, sharpness)
+
+
 def interp_wrapper(origin_grid, target_grid, var_name, i_use_xesmf=0,
                    nan_interp_kernel_radius=300000, nan_interp_sharpness=3):
-    """functions.py:1062-1141: dispatch per variable.  The NaN-ignoring Gaussian-kernel scheme
-    for ``tos``/``siconc`` (functions.py:900-1060) lives in un-vendored VTK code and is out of
-    scope of the CUDA path."""
+    """functions.py:1062-1141 on ``ncio.Dataset`` objects: ``tos`` and ``siconc`` (curvilinear ocean grid
+    with NaNs over land) take the NaN-ignoring Gaussian-kernel scheme (:900-1060), everything else the
+    bilinear regridding."""
     if var_name in ['tos', 'siconc']:
-        raise NotImplementedError("nan_ignoring_interp (pyvista/VTK) is not part of the CUDA path; "
-                                  "regrid tos/siconc with the reference and pass the result on")
+        land_fraction = np.asarray(target_grid["FR_LAND"].data)[0]                           # :1096
+        var = origin_grid[var_name]
+        lat_t = np.asarray(target_grid[LAT_ERA].data, dtype=np.float64)
+        lon_t = np.asarray(target_grid[LON_ERA].data, dtype=np.float64)
+        result = nan_ignoring_interp_arrays(land_fraction, lat_t, lon_t, var.data,
+                                            origin_grid[LAT_GCM_OCEAN].data, origin_grid[LON_GCM_OCEAN].data,
+                                            nan_interp_kernel_radius, nan_interp_sharpness)  # :1100-1107
+        ds = ncio.Dataset(attrs=dict(description=str(var_name) + " on ERA5 grid", units="K",
+                                     long_name=str(var_name)))                               # :1110-1135
+        ds[TIME_GCM_OCEAN] = origin_grid[TIME_GCM_OCEAN]
+        ds["lat"] = ncio.Variable(("lat",), lat_t, target_grid[LAT_ERA].attrs)
+        ds["lon"] = ncio.Variable(("lon",), lon_t, target_grid[LON_ERA].attrs)
+        ds[var_name] = ncio.Variable((TIME_GCM_OCEAN, "lat", "lon"), np.asarray(result, dtype=np.float64))
+        return ds
     return regrid_lat_lon(origin_grid, target_grid, var_name, method='bilinear', i_use_xesmf=i_use_xesmf)

@@ -7,7 +7,7 @@ tag=$1; shift
 root=$(cd "$(dirname "$0")/.." && pwd)
 d=$root/scratch/build_$tag
 mkdir -p $d
-for f in pgw_timestep pgw_column_tma pgw_staged pgw_ops pgw_step02 pgw_misc; do
+for f in pgw_timestep pgw_column_tma pgw_staged pgw_ops pgw_step02 pgw_nanterp pgw_misc; do
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -I$root/include "$@" \
        -c $root/pgw4era5_b200/csrc/$f.cu -o $d/$f.o &
 done

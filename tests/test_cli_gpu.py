@@ -113,6 +113,40 @@ def test_step_02_cli(tmp_path):
     np.testing.assert_array_equal(rg["lat"].data, tlat)
 
 
+def test_step_02_cli_ocean_variables(tmp_path):
+    """`regridding -v tos`: the curvilinear ocean grid goes through the NaN-ignoring Gaussian-kernel scheme
+    (functions.py:900-1060, :1093-1135); 12 monthly fields, NaN over GCM land and over ERA5 land."""
+    from oracle import pgw_oracle as O
+    from pgw4era5_b200 import step_02_preproc_deltas as S2
+    from test_nanterp import _ocean_case
+    glat, glon, vals3, tlat, tlon, land_fr, _ = _ocean_case(8, False)
+    rng = np.random.default_rng(62)
+    vals = np.concatenate([vals3] * 4, axis=0) + rng.normal(size=(12, 1, 1)).astype(np.float32)
+    gdir, rdir = tmp_path / "gcm", tmp_path / "regrid"
+    gdir.mkdir()
+    stamps = S.monthly_stamps()
+    for base in settings.file_name_bases.values():
+        ds = ncio.Dataset()
+        ds["time"] = ncio.encode_time(stamps, "days since 1850-01-01 00:00:00")
+        ds["latitude"] = ncio.Variable(("j", "i"), glat); ds["longitude"] = ncio.Variable(("j", "i"), glon)
+        ds["tos"] = ncio.Variable(("time", "j", "i"), vals)
+        ds.to_netcdf(str(gdir / base.format("tos")))
+    era = ncio.Dataset()
+    era["time"] = ncio.Variable(("time",), np.array([0.0]))
+    era["lat"] = ncio.Variable(("lat",), tlat); era["lon"] = ncio.Variable(("lon",), tlon)
+    era["FR_LAND"] = ncio.Variable(("time", "lat", "lon"), land_fr[None])
+    era.to_netcdf(str(tmp_path / "era.nc"))
+    S2.main(["regridding", "-i", str(gdir), "-o", str(rdir), "-e", str(tmp_path / "era.nc"), "-v", "tos"])
+    rg = ncio.open_dataset(str(rdir / "tos_delta.nc"))
+    assert rg["tos"].dims == ("time", "lat", "lon") and rg["tos"].data.shape == (12, len(tlat), len(tlon))
+    np.testing.assert_array_equal(rg["lat"].data, tlat)
+    for m in (0, 1, 11):
+        ref = O.nan_ignoring_interp(land_fr, tlat, tlon, vals[m], glat.copy(), glon.copy(),
+                                    settings.nan_interp_kernel_radius, settings.nan_interp_sharpness)
+        np.testing.assert_allclose(rg["tos"].data[m], ref, rtol=0, atol=1e-9, equal_nan=True)
+        assert np.all(np.isnan(rg["tos"].data[m][land_fr > 0.7]))
+
+
 def test_step_03_cli_pipelines_several_files(tmp_path):
     """Production mode over five files: reader thread -> HostPipeline (two CUDA streams) -> writer
     thread must give the same files as the one-file-at-a-time routine, in the right order."""

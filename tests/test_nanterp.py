@@ -1,0 +1,149 @@
+"""The NaN-ignoring Gaussian-kernel regridding of tos / siconc (functions.py:900-1060).
+
+PARITY UNPINNED against the reference's own third-party arithmetic (pyproj Geod.inv, pyvista/VTK point
+interpolation are neither vendored nor installed): the oracle restates the published algorithms and is
+checked here against closed forms, known WGS84 constants and an independent Vincenty inverse; the CUDA
+path is checked against the oracle."""
+import numpy as np
+import pytest
+
+from oracle import pgw_oracle as O
+
+
+def vincenty(lat1, lon1, lat2, lon2):
+    """Vincenty (1975) inverse formula on WGS84, independent of the oracle's quadrature."""
+    a, f = O.WGS84_A, O.WGS84_F
+    b = a * (1 - f)
+    U1, U2 = np.arctan((1 - f) * np.tan(np.radians(lat1))), np.arctan((1 - f) * np.tan(np.radians(lat2)))
+    L = np.radians(lon2 - lon1)
+    lam = L
+    for _ in range(500):
+        sl, cl = np.sin(lam), np.cos(lam)
+        ss = np.sqrt((np.cos(U2) * sl) ** 2 + (np.cos(U1) * np.sin(U2) - np.sin(U1) * np.cos(U2) * cl) ** 2)
+        cs = np.sin(U1) * np.sin(U2) + np.cos(U1) * np.cos(U2) * cl
+        sig = np.arctan2(ss, cs)
+        sa = np.cos(U1) * np.cos(U2) * sl / ss
+        c2a = 1 - sa ** 2
+        c2sm = cs - 2 * np.sin(U1) * np.sin(U2) / c2a
+        C = f / 16 * c2a * (4 + f * (4 - 3 * c2a))
+        new = L + (1 - C) * f * sa * (sig + C * ss * (c2sm + C * cs * (-1 + 2 * c2sm ** 2)))
+        if abs(new - lam) < 1e-14:
+            break
+        lam = new
+    u2 = c2a * (a * a - b * b) / (b * b)
+    A = 1 + u2 / 16384 * (4096 + u2 * (-768 + u2 * (320 - 175 * u2)))
+    B = u2 / 1024 * (256 + u2 * (-128 + u2 * (74 - 47 * u2)))
+    ds = B * ss * (c2sm + B / 4 * (cs * (-1 + 2 * c2sm ** 2) - B / 6 * c2sm * (-3 + 4 * ss ** 2) * (-3 + 4 * c2sm ** 2)))
+    return b * A * (sig - ds)
+
+
+def test_geodesic_known_values():
+    # WGS84 quarter meridian 10 001 965.729 m; a quarter of the equator = a pi / 2
+    assert abs(float(O.wgs84_meridian_arc(90.0)) - 10001965.7293) < 1e-3
+    assert abs(float(O.wgs84_same_lat_distance(0.0, 90.0)) - O.WGS84_A * np.pi / 2) < 1e-6
+    # antipodal points of the equator: over the pole; the equator itself up to (1 - f) 180 degrees
+    assert abs(float(O.wgs84_same_lat_distance(0.0, 180.0)) - 2 * float(O.wgs84_meridian_arc(90.0))) < 1e-6
+    assert abs(float(O.wgs84_same_lat_distance(0.0, 179.39)) - O.WGS84_A * np.radians(179.39)) < 1e-6
+    assert float(O.wgs84_same_lat_distance(0.0, 179.9)) < O.WGS84_A * np.radians(179.9)      # lifts off the equator
+    # Karney (2013), the equatorial near-antipodal example: (0, 0) -> (0, 179.5): 19 980 861.9 m  (his s12 for 179.5)
+    assert abs(float(O.wgs84_same_lat_distance(0.0, 179.5)) - 19980861.9) < 1.0
+    for lat in (10.0, 45.0, 80.0):
+        assert abs(float(O.wgs84_same_lat_distance(lat, 180.0)) - float(O.wgs84_half_turn_distance(lat))) < 1e-5
+    assert float(O.wgs84_same_lat_distance(33.0, 0.0)) == 0.0
+
+
+def test_geodesic_matches_vincenty():
+    rng = np.random.default_rng(0)
+    for _ in range(100):
+        lat, dl = rng.uniform(0.2, 89.0), rng.uniform(0.05, 176.0)
+        assert abs(float(O.wgs84_same_lat_distance(lat, dl)) - vincenty(lat, 0.0, lat, dl)) < 1e-3     # Vincenty: < 1 mm
+        assert abs(float(O.wgs84_meridian_arc(lat)) - vincenty(0.0, 7.0, lat, 7.0)) < 1e-3
+    lat_m, lon_m = O.lonlat_to_meter(np.array([-30.0, 30.0, 0.0]), np.array([-40.0, 40.0, 0.0]))
+    assert lat_m[0] == -lat_m[1] and lon_m[0] == -lon_m[1] and lat_m[2] == 0.0 and lon_m[2] == 0.0
+
+
+def test_gaussian_kernel_properties():
+    rng = np.random.default_rng(1)
+    src = rng.uniform(-1e6, 1e6, (200, 2))
+    dst = rng.uniform(-1e6, 1e6, (50, 2))
+    # a constant field stays constant wherever there is a point in the radius, NaN elsewhere
+    far = np.array([[5e6, 5e6]])
+    out = O.gaussian_kernel_interp(src, np.full(200, 3.5), np.vstack([dst, far]), 4e5, 4.0)
+    inside = ((dst[:, None, :] - src[None]) ** 2).sum(-1).min(axis=1) <= (4e5) ** 2
+    assert np.all(np.abs(out[:50][inside] - 3.5) < 1e-12) and np.all(np.isnan(out[:50][~inside])) and np.isnan(out[50])
+    # explicit weights, and an exact hit takes the value of that point
+    val = rng.normal(size=200)
+    d2 = ((dst[0] - src) ** 2).sum(-1)
+    w = np.where(d2 <= (6e5) ** 2, np.exp(-(4.0 / 6e5) ** 2 * d2), 0.0)
+    assert abs(O.gaussian_kernel_interp(src, val, dst[:1], 6e5, 4.0)[0] - (w * val).sum() / w.sum()) < 1e-12
+    assert O.gaussian_kernel_interp(src, val, src[17:18], 6e5, 4.0)[0] == val[17]
+
+
+def _ocean_case(seed, glob):
+    """A curvilinear 'ocean grid' (2-D lat/lon, NaN over 'land', NaNs that differ between months) and an
+    ERA5 target grid with a land fraction."""
+    rng = np.random.default_rng(seed)
+    if glob:
+        nj, ni = 24, 48
+        lat1, lon1 = np.linspace(-78, 88, nj), np.arange(ni) * 7.5 + 2.0          # 0..360, crosses 180
+        tlat, tlon = np.linspace(-90, 90, 19), np.arange(0.0, 360.0, 12.0)
+        radius = 1.5e6
+    else:
+        nj, ni = 30, 36
+        lat1, lon1 = np.linspace(25, 82, nj), np.linspace(-28, 58, ni)
+        tlat, tlon = np.linspace(30, 80, 21), np.linspace(-20, 50, 29)
+        radius = 1.0e6
+    glat, glon = np.meshgrid(lat1, lon1, indexing="ij")
+    glat = glat + 0.8 * np.sin(np.radians(glon) * 2)                              # distort: truly 2-D coordinates
+    glon = glon + 1.5 * np.cos(np.radians(glat) * 3)
+    if glob:
+        glon = np.mod(glon, 360.0)
+        glat = np.clip(glat, -89.0, 89.5)
+    vals = (2.0 + np.cos(np.radians(glat)) + 0.3 * rng.normal(size=(3, nj, ni))).astype(np.float32)
+    land = rng.uniform(size=(nj, ni)) < 0.25
+    vals[:, land] = np.nan
+    vals[1, rng.uniform(size=(nj, ni)) < 0.1] = np.nan                            # month-dependent gaps
+    land_fr = (rng.uniform(size=(len(tlat), len(tlon))) < 0.3).astype(np.float32) * rng.uniform(0.5, 1.0, (len(tlat), len(tlon))).astype(np.float32)
+    return glat, glon, vals, tlat, tlon, land_fr, radius
+
+
+def test_nan_ignoring_interp_oracle_wraps_the_dateline():
+    """the point cloud is replicated east and west (functions.py:978-988): a target at lon 180 sees both sides"""
+    glat, glon, vals, tlat, tlon, land_fr, radius = _ocean_case(5, True)
+    out = O.nan_ignoring_interp(land_fr * 0, tlat, tlon, vals[0], glat, glon, radius, 4.0)
+    j = int(np.argmin(np.abs(tlat - 0.0)))
+    i180 = int(np.argmin(np.abs(tlon - 180.0)))
+    assert np.isfinite(out[j, i180])
+    assert np.nanmin(out) >= np.nanmin(vals[0]) - 1e-9 and np.nanmax(out) <= np.nanmax(vals[0]) + 1e-9   # convex weights
+
+
+@pytest.mark.gpu
+def test_lonlat_to_meter_gpu():
+    from pgw4era5_b200 import functions as F
+    rng = np.random.default_rng(2)
+    lat = np.concatenate([rng.uniform(-89.9, 89.9, 500), [0.0, 0.0, 0.0, 0.0, 45.0, -45.0, 90.0, -90.0, 0.25]])
+    lon = np.concatenate([rng.uniform(-180, 360, 500), [0.0, 179.9, 180.0, 359.0, 180.0, 181.0, 10.0, 200.0, 179.75]])
+    lat_m, lon_m, ht = F.lonlat_to_meter(lon, lat, half_turn=True)
+    lon_w = np.where(lon > 180, lon - 360, lon)
+    r_lat, r_lon = O.lonlat_to_meter(lon_w, lat)
+    np.testing.assert_allclose(lat_m.cpu().numpy(), r_lat, rtol=0, atol=1e-6)
+    np.testing.assert_allclose(lon_m.cpu().numpy(), r_lon, rtol=0, atol=1e-5)
+    np.testing.assert_allclose(ht.cpu().numpy(), O.wgs84_half_turn_distance(lat), rtol=0, atol=1e-6)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("glob", [False, True])
+def test_nan_ignoring_interp_gpu_matches_oracle(glob):
+    from pgw4era5_b200 import functions as F
+    glat, glon, vals, tlat, tlon, land_fr, radius = _ocean_case(7 if glob else 6, glob)
+    out = F.nan_ignoring_interp_arrays(land_fr, tlat, tlon, vals, glat, glon, radius, 4.0)
+    assert out.shape == (3, len(tlat), len(tlon)) and out.dtype == np.float64
+    for m in range(3):
+        ref = O.nan_ignoring_interp(land_fr, tlat, tlon, vals[m], glat.copy(), glon.copy(), radius, 4.0)
+        assert np.array_equal(np.isnan(out[m]), np.isnan(ref)), m
+        assert np.isnan(ref).any() and np.isfinite(ref).sum() > 50
+        np.testing.assert_allclose(out[m], ref, rtol=0, atol=1e-9, equal_nan=True)
+    # an exact hit: a target on top of a source point takes its value
+    one = F.nan_ignoring_interp_arrays(np.zeros((1, 1), np.float32), glat[5, 7:8], glon[5, 7:8] if glon[5, 7] <= 180 else glon[5, 7:8] - 360,
+                                       np.where(np.isnan(vals[0]), 1.0, vals[0]), glat, glon, radius, 4.0)
+    assert abs(float(one[0, 0]) - float(np.where(np.isnan(vals[0]), 1.0, vals[0])[5, 7])) < 1e-12
