@@ -359,7 +359,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--grid", default="GL", choices=sorted(GRIDS))
     ap.add_argument("--ring", type=int, default=4)
-    ap.add_argument("--e2e-steps", type=int, default=24)
+    ap.add_argument("--e2e-steps", type=int, default=48)
     ap.add_argument("--e2e-slots", type=int, default=2, help="timesteps in flight in the host-buffer pipeline")
     ap.add_argument("--no-cpu", action="store_true")
     a = ap.parse_args()

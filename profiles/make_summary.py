@@ -18,6 +18,7 @@ launch = "; ".join("`%s` %.0f us x%d (%.1f %%)" % (k, sum(v) / len(v), len(v), 1
 step02 = json.load(open(os.path.join(ROOT, "profiles", "r1_step02.json")))
 files = json.load(open(os.path.join(ROOT, "profiles", "r1_files.json")))
 traffic = json.load(open(os.path.join(ROOT, "profiles", "column_kernel_traffic.json")))
+par = json.load(open(os.path.join(ROOT, "profiles", "r1_parity.json")))
 s = '''# Round 1 - measured numbers (B200, sm_100a, SM clock %(mhz).0f MHz, throttle reasons: %(reasons)s)
 
 All numbers from `bench.py` / `profiles/bench_*.py` on `gpurun` boxes of this pool; ncu evidence next to this file.
@@ -32,7 +33,7 @@ inputs cycling through 4 distinct device-resident timesteps (2.3 GB each >> 126 
 | algorithmic bytes per launch (SURVEY 8d) | 5 311.6 MB | `bench.algorithmic_bytes` |
 | achieved | %(ach).0f GB/s = **%(frac).3f** of the measured peak 6 535 GB/s (%(fracn).2f of nominal 8 TB/s) | same |
 | DRAM traffic per launch (ncu `dram__bytes_read+write`) | %(tr).2f GB (%(trr).2f R + %(trw).2f W) | `r1_column_kernel.md` |
-| end to end, host buffers, H2D+D2H inside (`e2e`) | %(e2e).1f timesteps/s (2.31 GB each way per step; PCIe moves that in 49.8 ms = 20.1/s at best) | same |
+| end to end, host buffers, H2D+D2H inside (`e2e`) | %(e2e).1f timesteps/s over %(e2esteps)d steps (2.31 GB each way per step, both PCIe directions busy: %(e2egb).1f GB/s each way) | same |
 | timesteps/s, 2xB200, timestep-sharded (weak) | %(n2).1f (delta broadcast %(bc).0f ms, once) | torchrun, %(n2steps)d steps (kernel of an earlier commit of the round) |
 | timesteps/s, 8xB200, timestep-sharded (weak) | %(n8).1f = 8 x %(n8p).1f (delta broadcast %(bc8).0f ms, once; BASELINE target: >= 4 922) | torchrun, %(n8steps)d steps per rank |
 | CPU baseline, oracle port, 1 host core | %(cpu).4f timesteps/s | `cpu_baseline` |
@@ -40,7 +41,9 @@ inputs cycling through 4 distinct device-resident timesteps (2.3 GB each >> 126 
 | iteration count | 6 in %(nit)d/%(nit)d steps, %(reruns)d reruns, %(rew)d rewrites (warm-up only) | `config.n_iter`, `config.engine` |
 | step_02 smoothing, one 3-D daily variable | %(sm_ms).2f ms = %(sm_g).0f GB/s (%(sm_f).2f of peak) | `bench_step02.py`, `r1_step02.json` |
 | step_02 regridding, one 3-D daily variable (28.8 GB out) | %(rg_ms).2f ms = %(rg_g).0f GB/s (%(rg_f).2f of peak) | same |
-| file -> file, EU files (126 MB), NetCDF-3 | %(fp).1f files/s pipelined vs %(fs).1f file by file | `bench_files.py`, `r1_files.json` |
+| step_02 ocean variables (tos/siconc), 12 monthly fields, 170x360 curvilinear -> 721x1440, radius 1000 km | %(oc_ms).1f ms for the whole call (coordinate mapping, sort, Gaussian-kernel pass) | same |
+| file -> file, EU files (126 MB), NetCDF-3 | %(fp).1f files/s pipelined without host decoding (%(fst).1f steady state over 96 files) vs %(fd).1f with the scipy codec in the same pipeline vs %(fs).1f file by file | `bench_files.py`, `r1_files.json` |
+| parity vs the executed reference (golden case, PS/FIS double) | ps %(p_ps).1e Pa, T %(p_t).1e K, QV %(p_q).1e; iterations identical for 4 settings | `parity_report.py`, `r1_parity.json` |
 
 Launch list of one bench run (`r1_launches.csv`, ncu `--metrics gpu__time_duration.sum --clock-control none -k regex:pgw`;
 cold-cache, serialised): %(launch)s.  `pgw_rewrite_kernel` only works in the two warm-up steps that over-predicted
@@ -51,7 +54,10 @@ shared-log walkers) -> 2.6 (fp32 stash, 3 CTAs/SM) -> 2.2 (batched prologue, nod
 1.99 (L2 node prefetch, iteration 0 folded into phase 1, consume-before-load walker steps) -> 1.69 (TMA pair ring with a
 producer warp, one float4 walker, one streaming loop: hot code 4 900 -> 600 SASS instructions, icache hit 94 -> 99.4 %%) ->
 1.63 (prefetch distances, incremental node offsets) -> 1.47 (fixed point through a polynomial in dps: the parked levels
-are integrated once, not once per iteration).
+are integrated once, not once per iteration) -> 1.46 (Rd*Tv of the ERA state in float32, as the reference forms it).
+Measured and dropped afterwards: e-only stash (1.65 ms at 3 CTAs/SM, 2.15 at 4 with 96 registers), setmaxnreg with the
+5-warp CTA (hangs), L2 prefetch of the successor CTA's prologue (1.55 ms with or without the prefetch enabled: the
+extra code alone costs 6 %%; the kernel sits on the 128-register edge).
 
 Tools: `summarize_ncu.py` (report -> markdown), `line_profile.py` (per-source-line instructions / stall samples, joins the
 ncu SASS page with `nvdisasm -g`), `gpu_cycle.sh` (tests + bench + capture in one `gpurun` call), `build_variant.sh`
@@ -65,6 +71,12 @@ ncu SASS page with `nvdisasm -g`), `gpu_cycle.sh` (tests + bench + capture in on
            reruns=d["config"]["engine"]["reruns"], rew=d["config"]["engine"]["rewrites"],
            sm_ms=step02["smoothing"]["ms"], sm_g=step02["smoothing"]["achieved_gbs"], sm_f=step02["smoothing"]["frac_of_peak"],
            rg_ms=step02["regridding"]["ms"], rg_g=step02["regridding"]["achieved_gbs"], rg_f=step02["regridding"]["frac_of_peak"],
-           fp=files["pipelined_files_per_s"], fs=files["file_by_file_files_per_s"], launch=launch)
+           fp=files["pipelined_files_per_s"], fs=files["file_by_file_files_per_s"], launch=launch,
+           fd=files["pipelined_decoding_files_per_s"], fst=files["steady_state_96_files"]["pipelined_files_per_s"],
+           oc_ms=step02["ocean_regridding"]["ms"], e2esteps=d["e2e"]["steps"],
+           e2egb=d["e2e"]["value"] * d["e2e"]["h2d_bytes_per_step"] / 1e9,
+           p_ps=par["vs_executed_reference"]["PS_FIS_double (default64)"]["PS"],
+           p_t=par["vs_executed_reference"]["PS_FIS_double (default64)"]["T"],
+           p_q=par["vs_executed_reference"]["PS_FIS_double (default64)"]["QV"])
 open(os.path.join(ROOT, "profiles", "r1_summary.md"), "w").write(s)
 print(s)
