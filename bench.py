@@ -205,6 +205,8 @@ def run_ours(a):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    from pgw4era5_b200.parallel import bind_to_gpu_numa
+    numa = None if os.environ.get("PGW_NO_NUMA_BIND") else bind_to_gpu_numa(local)    # before any pinned allocation
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
@@ -340,7 +342,7 @@ def run_ours(a):
                         "(BASELINE configs[0], not the metric's configuration)" % (ny, nx)),
                        "grid": a.grid, "ring": a.ring,
                        "l2": "inputs cycle through %d distinct 2.3 GB timesteps (>> 126 MB L2)" % a.ring,
-                       "parallelism": "timestep-sharded x%d" % world,
+                       "parallelism": "timestep-sharded x%d" % world, "numa_node": numa,
                        "n_iter": {"min": int(min(n_iters)), "max": int(max(n_iters)), "steps": len(n_iters)},
                        "engine": dict(eng.stats), "broadcast_ms": bcast_ms},
             "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,

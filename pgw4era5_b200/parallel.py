@@ -60,12 +60,48 @@ def broadcast_deltas(deltas, src=0, group=None):
     return e0.elapsed_time(e1)
 
 
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa(device_index):
+    """Pin this process to the CPUs of the NUMA node the GPU hangs off, BEFORE any pinned host buffer is
+    allocated: the staging buffers of the host pipeline are then node-local to the GPU's PCIe root, which is
+    what lets N processes stream over N PCIe links without meeting on the inter-socket link.  Returns the
+    node (or None when the topology is not exposed; nothing is changed then)."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(device_index)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/numa_node" % bdf) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            cpus = _parse_cpulist(f.read())
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except (OSError, AttributeError, ValueError, RuntimeError):
+        return None
+
+
 def _worker(payload):
     func, kwargs, worker_slot = payload
     try:
         import torch
         if torch.cuda.is_available():
-            torch.cuda.set_device(worker_slot % torch.cuda.device_count())
+            dev = worker_slot % torch.cuda.device_count()
+            torch.cuda.set_device(dev)
+            bind_to_gpu_numa(dev)
     except ImportError:
         pass
     return func(**kwargs)

@@ -34,7 +34,7 @@ inputs cycling through 4 distinct device-resident timesteps (2.3 GB each >> 126 
 | achieved | %(ach).0f GB/s = **%(frac).3f** of the measured peak 6 535 GB/s (%(fracn).2f of nominal 8 TB/s) | same |
 | DRAM traffic per launch (ncu `dram__bytes_read+write`) | %(tr).2f GB (%(trr).2f R + %(trw).2f W) | `r1_column_kernel.md` |
 | end to end, host buffers, H2D+D2H inside (`e2e`) | %(e2e).1f timesteps/s over %(e2esteps)d steps (2.31 GB each way per step, both PCIe directions busy: %(e2egb).1f GB/s each way) | same |
-| timesteps/s, 2xB200, timestep-sharded (weak) | %(n2).1f (delta broadcast %(bc).0f ms, once) | torchrun, %(n2steps)d steps (kernel of an earlier commit of the round) |
+| timesteps/s, 2xB200, timestep-sharded (weak) | %(n2).1f (delta broadcast %(bc).0f ms, once) | torchrun, %(n2steps)d steps per rank |
 | timesteps/s, 8xB200, timestep-sharded (weak) | %(n8).1f = 8 x %(n8p).1f (delta broadcast %(bc8).0f ms, once; BASELINE target: >= 4 922) | torchrun, %(n8steps)d steps per rank |
 | CPU baseline, oracle port, 1 host core | %(cpu).4f timesteps/s | `cpu_baseline` |
 | reference arm (`--impl reference`), oracle port on %(cores)d host cores | %(ref).3f timesteps/s | `bench.py --impl reference` |

@@ -171,3 +171,14 @@ def test_settings_surface():
     from pgw4era5_b200.step_03_apply_to_era import build_parser
     a = build_parser().parse_args(["-i", "a", "-o", "b", "-d", "c", "-t", "-p", "2", "-H", "6"])
     assert a.ignore_top_pressure_error and a.n_par == 2 and a.hour_inc_step == 6 and a.first_era_step == "2006080200"
+
+
+def test_numa_binding_helpers():
+    """parallel.bind_to_gpu_numa: cpulist parsing; without a GPU / exposed topology nothing changes."""
+    import os
+    from pgw4era5_b200.parallel import _parse_cpulist, bind_to_gpu_numa
+    assert _parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11} and _parse_cpulist("") == set()
+    before = os.sched_getaffinity(0)
+    import torch
+    if not torch.cuda.is_available():
+        assert bind_to_gpu_numa(0) is None and os.sched_getaffinity(0) == before
