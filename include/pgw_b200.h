@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PGW_B200_ABI_VERSION 4
+#define PGW_B200_ABI_VERSION 5   /* 5: + pgw_abi_version, pgw_integ_geopot_f64_f32, pgw_byteswap32, pgw_geod_to_meter_f64, pgw_gauss_interp_f64 */
 
 /* host-side return codes */
 #define PGW_OK               0
@@ -60,6 +60,7 @@ extern "C" {
 #define PGW_MAX_ITER   64
 
 const char *pgw_version(void);
+int pgw_abi_version(void);          /* PGW_B200_ABI_VERSION the library was built with */
 const char *pgw_last_error(void);      /* text of the last PGW_E_LAUNCH */
 
 /* ------------------------------------------------------------------------

@@ -55,6 +55,9 @@ class TimestepResult(C.Structure):
     _fields_ = [("n_iter", C.c_int), ("converged", C.c_int), ("rewritten", C.c_int), ("reserved", C.c_int)]
 
 
+ABI_VERSION = 5          # PGW_B200_ABI_VERSION of include/pgw_b200.h
+
+
 class NativeError(RuntimeError):
     pass
 
@@ -68,6 +71,7 @@ def _load():
     ll, i, d, vp = C.c_longlong, C.c_int, C.c_double, C.c_void_p
     sig = {
         "pgw_version": (C.c_char_p, []),
+        "pgw_abi_version": (i, []),
         "pgw_last_error": (C.c_char_p, []),
         "pgw_sizeof_timestep_args": (ll, []),
         "pgw_interp_logp_f64": (i, [vp, vp, vp, vp, i, i, i, ll, i, i, i, vp, vp]),
@@ -105,8 +109,15 @@ def _load():
         "pgw_ps_adjust_f64": (i, [vp, vp, vp, vp, vp, d, vp, vp, ll, vp]),
     }
     for name, (res, args) in sig.items():
-        fn = getattr(lib, name)
+        try:
+            fn = getattr(lib, name)
+        except AttributeError:
+            raise ImportError("%s does not export %s: stale build, run `python -m pgw4era5_b200.build`"
+                              % (LIB_PATH, name))
         fn.restype, fn.argtypes = res, args
+    if lib.pgw_abi_version() != ABI_VERSION:
+        raise ImportError("libpgw_b200.so has ABI %d, this package expects %d (include/pgw_b200.h): rebuild"
+                          % (lib.pgw_abi_version(), ABI_VERSION))
     if lib.pgw_sizeof_timestep_args() != C.sizeof(TimestepArgs):
         raise ImportError("pgw_timestep_args layout mismatch: C %d vs ctypes %d"
                           % (lib.pgw_sizeof_timestep_args(), C.sizeof(TimestepArgs)))

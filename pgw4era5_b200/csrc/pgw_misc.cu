@@ -23,7 +23,10 @@ int pgw_check_launch(const char *what) {
 }
 
 extern "C" {
-const char *pgw_version(void) { return "pgw_b200 0.2.0 (sm_100a, abi 2)"; }
+#define PGW_STR2(x) #x
+#define PGW_STR(x) PGW_STR2(x)
+const char *pgw_version(void) { return "pgw_b200 0.3.0 (sm_100a, abi " PGW_STR(PGW_B200_ABI_VERSION) ")"; }
+int pgw_abi_version(void) { return PGW_B200_ABI_VERSION; }
 const char *pgw_last_error(void) { return g_last_error; }
 long long pgw_sizeof_timestep_args(void) { return (long long)sizeof(pgw_timestep_args); }
 }

@@ -13,6 +13,7 @@ from pathlib import Path
 
 from . import ncio, settings
 from .functions import filter_data, interp_wrapper
+from .parallel import IterMP
 
 
 def build_parser():
@@ -28,7 +29,30 @@ def build_parser():
     parser.add_argument('-v', '--var_names', type=str,
                         default='ta,hur,ua,va,zg,hurs,tas,ps,tos,ts,siconc',
                         help='Comma-separated variable names to process.')
+    # not in the reference (which processes the files one after the other on the CPU): the
+    # (variable, HIST | SCEN-HIST) files are independent, so they are dealt out to worker processes,
+    # worker i on GPU i % device_count
+    parser.add_argument('-p', '--n_par', type=int, default=1,
+                        help='Number of worker processes (one per GPU) over which the files are distributed.')
     return parser
+
+
+def process_file(processing_step, inp_file, out_file, var_name, era5_file_path):
+    """One (variable, climate period) file: step_02_preproc_deltas.py:128-149."""
+    if processing_step == 'smoothing':
+        filter_data(inp_file, var_name, out_file)
+        return out_file
+    ds_era5 = ncio.open_dataset(era5_file_path)
+    try:
+        ds_gcm = ncio.open_dataset(inp_file)
+    except Exception:
+        raise RuntimeError("Files for variable " + var_name + " are missing")
+    ds_gcm = interp_wrapper(ds_gcm, ds_era5, var_name,
+                            i_use_xesmf=settings.i_use_xesmf_regridding,
+                            nan_interp_kernel_radius=settings.nan_interp_kernel_radius,
+                            nan_interp_sharpness=settings.nan_interp_sharpness)
+    ds_gcm.to_netcdf(out_file)
+    return out_file
 
 
 def main(argv=None):
@@ -43,25 +67,16 @@ def main(argv=None):
     Path(args.output_dir).mkdir(exist_ok=True, parents=True)
     var_names = args.var_names.split(',')
     print('Run {} for variable names {}.'.format(args.processing_step, var_names))
-    ds_era5 = ncio.open_dataset(args.era5_file_path) if args.era5_file_path else None
+    tasks = []
     for var_name in var_names:
         print(var_name)
         for clim_period in ['HIST', 'SCEN-HIST']:                  # step_02_preproc_deltas.py:116-121
             var_file_name = settings.file_name_bases[clim_period].format(var_name)
-            inp_file = os.path.join(args.input_dir, var_file_name)
-            out_file = os.path.join(args.output_dir, var_file_name)
-            if args.processing_step == 'smoothing':
-                filter_data(inp_file, var_name, out_file)
-            else:
-                try:
-                    ds_gcm = ncio.open_dataset(inp_file)
-                except Exception:
-                    raise RuntimeError("Files for variable " + var_name + " are missing")
-                ds_gcm = interp_wrapper(ds_gcm, ds_era5, var_name,
-                                        i_use_xesmf=settings.i_use_xesmf_regridding,
-                                        nan_interp_kernel_radius=settings.nan_interp_kernel_radius,
-                                        nan_interp_sharpness=settings.nan_interp_sharpness)
-                ds_gcm.to_netcdf(out_file)
+            tasks.append(dict(inp_file=os.path.join(args.input_dir, var_file_name),
+                              out_file=os.path.join(args.output_dir, var_file_name), var_name=var_name))
+    IMP = IterMP(njobs=args.n_par, run_async=True)
+    IMP.run(process_file, dict(processing_step=args.processing_step, era5_file_path=args.era5_file_path), tasks)
+    return IMP.output
 
 
 if __name__ == "__main__":

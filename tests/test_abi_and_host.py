@@ -28,6 +28,12 @@ def test_library_exports_every_declared_symbol():
     assert set(declared) <= set(N.EXPORTED) | {"pgw_version", "pgw_last_error"}
     assert N.lib.pgw_version().startswith(b"pgw_b200")
     assert N.lib.pgw_sizeof_timestep_args() == ctypes.sizeof(N.TimestepArgs)
+    # the header's ABI number is what the library reports and what the binding expects
+    import re
+    hdr = open(os.path.join(os.path.dirname(__file__), "..", "include", "pgw_b200.h")).read()
+    ver = int(re.search(r"#define PGW_B200_ABI_VERSION (\d+)", hdr).group(1))
+    assert N.lib.pgw_abi_version() == ver == N.ABI_VERSION
+    assert ("abi %d" % ver).encode() in N.lib.pgw_version()
 
 
 def test_invalid_arguments_are_rejected_without_a_gpu():

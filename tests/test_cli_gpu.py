@@ -111,6 +111,13 @@ def test_step_02_cli(tmp_path):
     assert rg["ta"].data.shape == (365, 3, 37, 72)
     np.testing.assert_allclose(rg["ta"].data, O.regrid_lat_lon(sm, lat, lon, tlat, tlon), rtol=0, atol=1e-6)
     np.testing.assert_array_equal(rg["lat"].data, tlat)
+    # -p 2: the (variable, period) files dealt out to two worker processes (worker i on GPU i % device_count)
+    out = S2.main(["regridding", "-i", str(sdir), "-o", str(tmp_path / "regrid_p2"), "-e", str(tmp_path / "era.nc"),
+                   "-v", "ta", "-p", "2"])
+    assert [os.path.basename(o) for o in out] == ["ta_historical.nc", "ta_delta.nc"]
+    for name in ("ta_historical.nc", "ta_delta.nc"):
+        np.testing.assert_array_equal(ncio.open_dataset(str(tmp_path / "regrid_p2" / name))["ta"].data,
+                                      ncio.open_dataset(str(rdir / name))["ta"].data)
 
 
 def test_step_02_cli_ocean_variables(tmp_path):
