@@ -39,11 +39,11 @@ inputs cycling through 4 distinct device-resident timesteps (2.3 GB each >> 126 
 | CPU baseline, oracle port, 1 host core | %(cpu).4f timesteps/s | `cpu_baseline` |
 | reference arm (`--impl reference`), oracle port on %(cores)d host cores | %(ref).3f timesteps/s | `bench.py --impl reference` |
 | iteration count | 6 in %(nit)d/%(nit)d steps, %(reruns)d reruns, %(rew)d rewrites (warm-up only) | `config.n_iter`, `config.engine` |
-| step_02 smoothing, one 3-D daily variable | %(sm_ms).2f ms = %(sm_g).0f GB/s (%(sm_f).2f of peak) | `bench_step02.py`, `r1_step02.json` |
+| step_02 smoothing, one 3-D daily variable | %(sm_ms).2f ms = %(sm_g).0f GB/s (%(sm_f).2f of peak) | `tests/bench_step02.py`, `r1_step02.json` |
 | step_02 regridding, one 3-D daily variable (28.8 GB out) | %(rg_ms).2f ms = %(rg_g).0f GB/s (%(rg_f).2f of peak) | same |
 | step_02 ocean variables (tos/siconc), 12 monthly fields, 170x360 curvilinear -> 721x1440, radius 1000 km | %(oc_ms).1f ms for the whole call (coordinate mapping, sort, Gaussian-kernel pass) | same |
-| file -> file, EU files (126 MB), NetCDF-3 | %(fp).1f files/s pipelined without host decoding (%(fst).1f steady state over 96 files) vs %(fd).1f with the scipy codec in the same pipeline vs %(fs).1f file by file | `bench_files.py`, `r1_files.json` |
-| parity vs the executed reference (golden case, PS/FIS double) | ps %(p_ps).1e Pa, T %(p_t).1e K, QV %(p_q).1e; iterations identical for 4 settings | `parity_report.py`, `r1_parity.json` |
+| file -> file, EU files (126 MB), NetCDF-3 | %(fp).1f files/s pipelined without host decoding (%(fst).1f steady state over 96 files) vs %(fd).1f with the scipy codec in the same pipeline vs %(fs).1f file by file | `tests/bench_files.py`, `r1_files.json` |
+| parity vs the executed reference (golden case, PS/FIS double) | ps %(p_ps).1e Pa, T %(p_t).1e K, QV %(p_q).1e; iterations identical for 4 settings | `tests/parity_report.py`, `r1_parity.json` |
 
 Launch list of one bench run (`r1_launches.csv`, ncu `--metrics gpu__time_duration.sum --clock-control none -k regex:pgw`;
 cold-cache, serialised): %(launch)s.  `pgw_rewrite_kernel` only works in the two warm-up steps that over-predicted

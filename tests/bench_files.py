@@ -5,7 +5,7 @@ File -> file throughput of the step_03 drop-in: N syntheti
 once file by file (read, H2D, pass, D2H, write in sequence) and once with the three-stage pipeline
 (reader thread / HostPipeline / writer thread).  Prints one JSON line.
 
-    python profiles/bench_files.py [--files 12] [--dir /tmp/pgw_files]
+    python tests/bench_files.py [--files 12] [--dir /tmp/pgw_files]
 """
 import argparse
 import json

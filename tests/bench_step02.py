@@ -5,7 +5,7 @@ delta variable (365 days x 19 plevs) from a 1 degree GCM grid (180 x 360) to the
 grid (721 x 1440).  Device-resident in/out, CUDA events, achieved GB/s on the algorithmic bytes
 (smoothing 2 x field, regridding field + 16 x field) against the measured HBM peak.
 
-    python profiles/bench_step02.py [--days 365] [--reps 5]
+    python tests/bench_step02.py [--days 365] [--reps 5]
 """
 import argparse
 import ctypes as C

@@ -6,7 +6,7 @@ Parity numbers of the round (needs a GPU): max |CUDA - reference| per output fie
   * against the oracle on BASELINE configs[0] (201 x 281 x 137).
 Prints one JSON object.
 
-    python profiles/parity_report.py > profiles/r1_parity.json
+    python tests/parity_report.py > profiles/r1_parity.json
 """
 import json
 import os
