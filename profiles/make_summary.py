@@ -19,6 +19,7 @@ step02 = json.load(open(os.path.join(ROOT, "profiles", "r1_step02.json")))
 files = json.load(open(os.path.join(ROOT, "profiles", "r1_files.json")))
 traffic = json.load(open(os.path.join(ROOT, "profiles", "column_kernel_traffic.json")))
 par = json.load(open(os.path.join(ROOT, "profiles", "r1_parity.json")))
+lb = json.load(open(os.path.join(ROOT, "profiles", "r1_latband.json")))
 s = '''# Round 1 - measured numbers (B200, sm_100a, SM clock %(mhz).0f MHz, throttle reasons: %(reasons)s)
 
 All numbers from `bench.py` / `profiles/bench_*.py` on `gpurun` boxes of this pool; ncu evidence next to this file.
@@ -36,6 +37,7 @@ inputs cycling through 4 distinct device-resident timesteps (2.3 GB each >> 126 
 | end to end, host buffers, H2D+D2H inside (`e2e`) | %(e2e).1f timesteps/s over %(e2esteps)d steps (2.31 GB each way per step, both PCIe directions busy: %(e2egb).1f GB/s each way) | same |
 | timesteps/s, 2xB200, timestep-sharded (weak) | %(n2).1f (delta broadcast %(bc).0f ms, once) | torchrun, %(n2steps)d steps per rank |
 | timesteps/s, 8xB200, timestep-sharded (weak) | %(n8).1f = 8 x %(n8p).1f (delta broadcast %(bc8).0f ms, once; BASELINE target: >= 4 922) | torchrun, %(n8steps)d steps per rank |
+| one global snapshot in 8 latitude bands, plev37, thresh 1e-3 (BASELINE configs[4], strong scaling) | %(lb_ms).2f ms per snapshot, %(lb_it)d iterations = the whole-grid oracle's count on the parity case | `tests/multigpu_latband.py --config5 --global-bench 50`, `r1_latband.json` |
 | CPU baseline, oracle port, 1 host core | %(cpu).4f timesteps/s | `cpu_baseline` |
 | reference arm (`--impl reference`), oracle port on %(cores)d host cores | %(ref).3f timesteps/s | `bench.py --impl reference` |
 | iteration count | 6 in %(nit)d/%(nit)d steps, %(reruns)d reruns, %(rew)d rewrites (warm-up only) | `config.n_iter`, `config.engine` |
@@ -73,7 +75,7 @@ ncu SASS page with `nvdisasm -g`), `gpu_cycle.sh` (tests + bench + capture in on
            rg_ms=step02["regridding"]["ms"], rg_g=step02["regridding"]["achieved_gbs"], rg_f=step02["regridding"]["frac_of_peak"],
            fp=files["pipelined_files_per_s"], fs=files["file_by_file_files_per_s"], launch=launch,
            fd=files["pipelined_decoding_files_per_s"], fst=files["steady_state_96_files"]["pipelined_files_per_s"],
-           oc_ms=step02["ocean_regridding"]["ms"], e2esteps=d["e2e"]["steps"],
+           oc_ms=step02["ocean_regridding"]["ms"], lb_ms=lb["ms_per_snapshot"], lb_it=lb["n_iter"], e2esteps=d["e2e"]["steps"],
            e2egb=d["e2e"]["value"] * d["e2e"]["h2d_bytes_per_step"] / 1e9,
            p_ps=par["vs_executed_reference"]["PS_FIS_double (default64)"]["PS"],
            p_t=par["vs_executed_reference"]["PS_FIS_double (default64)"]["T"],

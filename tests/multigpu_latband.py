@@ -30,8 +30,18 @@ def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
     dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
+    import argparse
+    from pgw4era5_b200 import synthetic as S
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config5", action="store_true", help="plev37 deltas and thresh 1e-3 (BASELINE configs[4])")
+    ap.add_argument("--global-bench", type=int, default=0, metavar="N",
+                    help="also time N snapshots of the full 721 x 1440 grid, one latitude band per rank")
+    a = ap.parse_args()
+    if a.config5:
+        settings.thresh_phi_ref_max_error = 1e-3
+    okw = dict(thresh_phi_ref_max_error=1e-3) if a.config5 else {}
     ny, nx = 48, 96
-    era, deltas = make_case(ny, nx, 3, region="GL")
+    era, deltas = make_case(ny, nx, 3, region="GL", plev=S.PLEV37 if a.config5 else S.PLEV19)
     r0, r1 = P.split_rows(ny, world)[rank]
     sub = {k: (v[..., r0:r1, :].contiguous().cuda() if isinstance(v, torch.Tensor) and v.dim() >= 3 else v)
            for k, v in era.items()}
@@ -39,7 +49,7 @@ def main():
     eng = PGWEngine(era["ak"], era["bk"], DeltaSet(subd, device="cuda"), soil1=era["soil1"],
                     group=dist.group.WORLD)
     res = eng.apply(sub, ERA_DATE, ignore_top_pressure_error=True)
-    ref = run_oracle(era, deltas)
+    ref = run_oracle(era, deltas, **okw)
     assert res["n_iter"] == ref["n_iter"], (rank, res["n_iter"], ref["n_iter"])
     for name in ("PS", "T", "QV", "U", "V", "T_SKIN"):
         g = res[name].cpu().numpy().astype(np.float64)
@@ -50,6 +60,37 @@ def main():
     print("rank %d rows %d..%d: n_iter %d == global oracle %d, fields within tolerance"
           % (rank, r0, r1, res["n_iter"], ref["n_iter"]), flush=True)
     dist.barrier()
+    if a.global_bench:
+        # one snapshot of the global grid, rows split over the ranks; the synthetic bands are generated per
+        # rank on the device (timing only; parity of the band scheme is what the part above checks)
+        NY, NX = 721, 1440
+        b0, b1 = P.split_rows(NY, world)[rank]
+        lat = np.linspace(-90.0, 90.0, NY)[b0:b1]
+        lon = np.arange(NX) * 0.25
+        plev = S.PLEV37 if a.config5 else S.PLEV19
+        e = S.make_era5(b1 - b0, NX, 100 + rank, device="cuda", lat=lat, lon=lon)
+        d = S.make_deltas(e, 100 + rank, plev=plev, device="cuda")
+        engb = PGWEngine(e["ak"], e["bk"], DeltaSet(d, device="cuda"), soil1=e["soil1"], group=dist.group.WORLD)
+        out = engb.alloc_outputs(b1 - b0, NX, len(e["soil1"]))
+        for _ in range(3):
+            r = engb.apply(e, ERA_DATE, out=out, ignore_top_pressure_error=True)
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(a.global_bench):
+            r = engb.apply(e, ERA_DATE, out=out, ignore_top_pressure_error=True)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / a.global_bench], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            import json
+            print(json.dumps({"workload": "one global 721x1440x137 snapshot, %d latitude bands, %s, thresh %g"
+                                          % (world, "plev37" if a.config5 else "plev19",
+                                             settings.thresh_phi_ref_max_error),
+                              "n_gpus": world, "ms_per_snapshot": float(t.item()), "n_iter": int(r["n_iter"]),
+                              "snapshots_per_s": 1000.0 / float(t.item())}), flush=True)
     dist.destroy_process_group()
 
 
