@@ -37,7 +37,7 @@ inputs cycling through 4 distinct device-resident timesteps (2.3 GB each >> 126 
 | end to end, host buffers, H2D+D2H inside (`e2e`) | %(e2e).1f timesteps/s over %(e2esteps)d steps (2.31 GB each way per step, both PCIe directions busy: %(e2egb).1f GB/s each way) | same |
 | timesteps/s, 2xB200, timestep-sharded (weak) | %(n2).1f (delta broadcast %(bc).0f ms, once) | torchrun, %(n2steps)d steps per rank |
 | timesteps/s, 8xB200, timestep-sharded (weak) | %(n8).1f = 8 x %(n8p).1f (delta broadcast %(bc8).0f ms, once; BASELINE target: >= 4 922) | torchrun, %(n8steps)d steps per rank |
-| one global snapshot in 8 latitude bands, plev37, thresh 1e-3 (BASELINE configs[4], strong scaling) | %(lb_ms).2f ms per snapshot, %(lb_it)d iterations = the whole-grid oracle's count on the parity case | `tests/multigpu_latband.py --config5 --global-bench 50`, `r1_latband.json` |
+| one global snapshot in 8 latitude bands, plev37, thresh 1e-3 (BASELINE configs[4], strong scaling) | %(lb_ms).2f ms per snapshot, %(lb_it)d iterations; on the small parity case every band stops at the whole-grid oracle's count (8) | `tests/multigpu_latband.py --config5 --global-bench 50`, `r1_latband.json` |
 | CPU baseline, oracle port, 1 host core | %(cpu).4f timesteps/s | `cpu_baseline` |
 | reference arm (`--impl reference`), oracle port on %(cores)d host cores | %(ref).3f timesteps/s | `bench.py --impl reference` |
 | iteration count | 6 in %(nit)d/%(nit)d steps, %(reruns)d reruns, %(rew)d rewrites (warm-up only) | `config.n_iter`, `config.engine` |
