@@ -139,7 +139,22 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+#ifndef PGW_WAIT_HINT_NS
+#define PGW_WAIT_HINT_NS 0
+#endif
+// Column-warp wait.  A failed try_wait costs three issue slots (SYNCS + 2 BRA) of an issue-bound kernel, so
+// the poll may carry a suspend-time hint: the warp then sleeps in hardware until the phase completes or the
+// time is up instead of returning after the (short) default limit.
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+#if PGW_WAIT_HINT_NS > 0
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "PGW_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra PGW_DONE;\n\t"
+        "bra PGW_WAIT;\n\t"
+        "PGW_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)PGW_WAIT_HINT_NS) : "memory");
+#else
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "PGW_WAIT:\n\t"
@@ -147,7 +162,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "@p bra PGW_DONE;\n\t"
         "bra PGW_WAIT;\n\t"
         "PGW_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+#endif
 }
+#ifndef PGW_PRODUCER_SLEEP_NS
+#define PGW_PRODUCER_SLEEP_NS 64
+#endif
+#define PGW_STR2_(x) #x
+#define PGW_STR_(x) PGW_STR2_(x)
 // Producer-side wait: suspend in hardware and back off between polls so that the lone
 // producer thread does not take issue slots from the column warps.
 __device__ __forceinline__ void mbar_wait_backoff(uint64_t *bar, uint32_t parity) {
@@ -156,7 +177,7 @@ __device__ __forceinline__ void mbar_wait_backoff(uint64_t *bar, uint32_t parity
         "PGW_WAITB:\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
         "@p bra PGW_DONEB;\n\t"
-        "nanosleep.u32 64;\n\t"
+        "nanosleep.u32 " PGW_STR_(PGW_PRODUCER_SLEEP_NS) ";\n\t"
         "bra PGW_WAITB;\n\t"
         "PGW_DONEB:\n\t}" ::"r"(smem_u32(bar)), "r"(parity), "r"(100000u) : "memory");
 }

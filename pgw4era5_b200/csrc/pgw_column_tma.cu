@@ -162,7 +162,7 @@ pgw_column_tma_kernel(const __grid_constant__ pgw_timestep_args a, const __grid_
     // Downward merge walk over the pressure-ascending nodes: state = lo node (index, pressure,
     // values of the four variables) and the differences to the hi node; inv_w == 0 encodes
     // "no interpolation" (at/after the last node, or above node 0): the lo values are returned.
-    // Nodes lo-1 and lo-2 are prefetched as raw (before, after) time slabs and blended when used;
+    // Node lo-1 is kept blended, node lo-2 as raw (before, after) time slabs that are blended one step after their loads;
     // nodes further down are pulled into L2.
     const float w_t = slab_weight(a.d4);
     const float4 *const d4lo = reinterpret_cast<const float4 *>(a.d4.lo);
@@ -202,7 +202,8 @@ pgw_column_tma_kernel(const __grid_constant__ pgw_timestep_args a, const __grid_
     const F4 rh0 = ldg4(d4lo + node_off(j_hi)), rh1 = ldg4(d4hi + node_off(j_hi));
     const int j_s1 = s_node >= 1 ? s_node - 1 : 0;
     const F4 rs0 = ldg4(d4lo + node_off(j_s1)), rs1 = ldg4(d4hi + node_off(j_s1));
-    F4 n0{0.f, 0.f, 0.f, 0.f}, n1 = n0, m0 = n0, m1 = n0;       // raw slabs of nodes lo-1, lo-2
+    // node lo-1 (raw here, kept blended in the walker state) and the raw slabs of node lo-2
+    F4 n0{0.f, 0.f, 0.f, 0.f}, n1 = n0, m0 = n0, m1 = n0;
     if (w_lo >= 1) { n0 = ldg4(d4lo + node_off(w_lo - 1)); n1 = ldg4(d4hi + node_off(w_lo - 1)); }
     if (w_lo >= 2) { m0 = ldg4(d4lo + node_off(w_lo - 2)); m1 = ldg4(d4hi + node_off(w_lo - 2)); }
 #pragma unroll
@@ -236,6 +237,7 @@ pgw_column_tma_kernel(const __grid_constant__ pgw_timestep_args a, const __grid_
     // walker state
     float w_p_lo, w_inv_p_lo, w_inv_w;
     F4 x_lo = blend4(rl0, rl1), x_d{0.f, 0.f, 0.f, 0.f};
+    F4 nb = blend4(n0, n1);                                     // node lo-1, blended
     if (w_lo >= 0) {
         w_p_lo = s_plev[w_lo]; w_inv_p_lo = s_inv_plev[w_lo]; w_inv_w = s_inv_w[w_lo];   // inv_w[K-1] == 0
         if (w_lo + 1 < K) {
@@ -271,11 +273,12 @@ pgw_column_tma_kernel(const __grid_constant__ pgw_timestep_args a, const __grid_
             --w_lo;
             if (w_lo >= 0) {
                 w_p_lo = s_plev[w_lo]; w_inv_p_lo = s_inv_plev[w_lo]; w_inv_w = s_inv_w[w_lo];
-                x_lo = blend4(n0, n1);
+                x_lo = nb;
                 x_d = F4{hi.x - x_lo.x, hi.y - x_lo.y, hi.z - x_lo.z, hi.w - x_lo.w};
-                n0 = m0; n1 = m1;
+                // the node after: blended now, one walker step after its loads were issued (their first use)
+                nb = blend4(m0, m1);
                 // the new loads are ordered behind the reads of the registers they replace
-                const int zero = reg_fence(n1.x, n1.y, n1.z, n1.w);
+                const int zero = reg_fence(nb.x, nb.y, nb.z, nb.w);
                 off_m += off_step;
                 if (w_lo >= 2) { m0 = ldg4(d4lo + off_m + zero); m1 = ldg4(d4hi + off_m + zero); }
                 if (w_lo >= kL2Ahead) {
