@@ -58,13 +58,19 @@ struct TmaParams {
 struct F4 { float x, y, z, w; };
 __device__ __forceinline__ F4 ldg4(const float4 *p) { const float4 v = __ldg(p); return F4{v.x, v.y, v.z, v.w}; }
 
-template <bool FAST>
+// NLEV_C / NP_C: number of levels and of parked levels as compile-time constants (0 = taken from the
+// arguments).  The loop bounds of the sweep are then immediates; with run-time bounds every pair iteration
+// waits on a constant-bank load before it can resolve its branches.  The host picks the instance that
+// matches (137 levels with 56 parked ones: ERA5 L137, p_ref = 300 hPa) or the generic one.
+template <bool FAST, int NLEV_C, int NP_C>
 __global__ void __launch_bounds__(kColumnThreads + 32, 3)
 pgw_column_tma_kernel(const __grid_constant__ pgw_timestep_args a, const __grid_constant__ TmaParams tp,
-                      const int lst, const int np) {
+                      const int lst_arg, const int np_arg) {
     constexpr int NT = kColumnThreads;
     extern __shared__ __align__(1024) unsigned char smem[];
-    const int L = a.nlev, K = a.nplev;
+    const int L = NLEV_C ? NLEV_C : a.nlev, K = a.nplev;
+    const int np = NP_C ? NP_C : np_arg;
+    const int lst = NLEV_C ? NLEV_C - NP_C : lst_arg;
     // ---- shared memory: pair ring | stash | (ak,bk)[np+1] | (akm,bkm)[np] | plev tables | barriers
     float *const ring = reinterpret_cast<float *>(smem);                          // [kTmaSlots][4][2][NT]
     float2 *const st_Te = reinterpret_cast<float2 *>(ring + kTmaSlots * 8 * NT);    // [np][NT] (T_pgw fp32, e_pgw)
@@ -627,9 +633,11 @@ int pgw_launch_column_tma(const pgw_timestep_args *a, const pgw_column_plan &pla
     }
     for (int l = 0; l < pgw::kTmaMaxLev; ++l)
         tp.m[l] = l < a->nlev ? make_float2((float)a->akm_host[l], (float)a->bkm_host[l]) : make_float2(0.f, 0.f);
-    auto kern = plan.fast ? pgw::pgw_column_tma_kernel<true> : pgw::pgw_column_tma_kernel<false>;
-    static thread_local size_t configured[2] = {0, 0};
-    size_t &conf = configured[plan.fast ? 1 : 0];
+    const bool l137 = a->nlev == 137 && plan.np == 56 && plan.lst == 137 - 56;
+    auto kern = plan.fast ? (l137 ? pgw::pgw_column_tma_kernel<true, 137, 56> : pgw::pgw_column_tma_kernel<true, 0, 0>)
+                          : (l137 ? pgw::pgw_column_tma_kernel<false, 137, 56> : pgw::pgw_column_tma_kernel<false, 0, 0>);
+    static thread_local size_t configured[4] = {0, 0, 0, 0};
+    size_t &conf = configured[(plan.fast ? 1 : 0) + (l137 ? 2 : 0)];
     if (plan.smem > conf) {
         int dev = 0, max_optin = 0;
         cudaGetDevice(&dev);
