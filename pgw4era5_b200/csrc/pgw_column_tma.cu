@@ -273,25 +273,35 @@ pgw_column_tma_kernel(const __grid_constant__ pgw_timestep_args a, const __grid_
     // element offset of node w_lo - 2 (the next one to fetch); one node down = +-ncol in the file
     const int32_t off_step = desc ? (int32_t)n : -(int32_t)n;
     uint32_t off_m = node_off(w_lo >= 2 ? w_lo - 2 : 0);
+    // A step only switches the bracket (x_lo <- nb); bringing nb and the raw slabs up to date (`refresh`) is
+    // deferred to ONE place per pair iteration, after both walks.  The lanes of a warp cross a node at
+    // different levels, and the scoreboard tracks registers per warp: with the loads issued inside the step,
+    // the step of the next lanes (same iteration, or the next one) waited on loads it did not need.  Now the
+    // first use of a load is at least one whole pair iteration after its issue.
+    bool stale = false;
+    auto refresh = [&]() {
+        nb = blend4(m0, m1);                                    // node w_lo-1: first use of its loads
+        // the new loads are ordered behind the reads of the registers they replace
+        const int zero = reg_fence(nb.x, nb.y, nb.z, nb.w);
+        off_m += off_step;
+        if (w_lo >= 2) { m0 = ldg4(d4lo + off_m + zero); m1 = ldg4(d4hi + off_m + zero); }
+        if (w_lo >= kL2Ahead) {
+            const uint32_t off = off_m + (uint32_t)((kL2Ahead - 2) * off_step);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(d4lo + off));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(d4hi + off));
+        }
+        stale = false;
+    };
     auto step_to = [&](float p) {
         while (w_p_lo > p) {
+            if (stale) refresh();                               // a second step within one pair iteration (rare)
             const F4 hi = x_lo;
             --w_lo;
             if (w_lo >= 0) {
                 w_p_lo = s_plev[w_lo]; w_inv_p_lo = s_inv_plev[w_lo]; w_inv_w = s_inv_w[w_lo];
                 x_lo = nb;
                 x_d = F4{hi.x - x_lo.x, hi.y - x_lo.y, hi.z - x_lo.z, hi.w - x_lo.w};
-                // the node after: blended now, one walker step after its loads were issued (their first use)
-                nb = blend4(m0, m1);
-                // the new loads are ordered behind the reads of the registers they replace
-                const int zero = reg_fence(nb.x, nb.y, nb.z, nb.w);
-                off_m += off_step;
-                if (w_lo >= 2) { m0 = ldg4(d4lo + off_m + zero); m1 = ldg4(d4hi + off_m + zero); }
-                if (w_lo >= kL2Ahead) {
-                    const uint32_t off = off_m + (uint32_t)((kL2Ahead - 2) * off_step);
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(d4lo + off));
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(d4hi + off));
-                }
+                stale = true;
             } else {
                 // above node 0: constant extrapolation with node 0's values; p_lo = 0 ends the walk
                 x_d = F4{0.f, 0.f, 0.f, 0.f}; w_inv_w = 0.0f; w_p_lo = 0.0f; w_inv_p_lo = 1.0f;
@@ -515,6 +525,7 @@ pgw_column_tma_kernel(const __grid_constant__ pgw_timestep_args a, const __grid_
         const float p0 = fmaf(ps_f, mm0.y, mm0.x), p1 = fmaf(ps_f, mm1.y, mm1.x);
         Dlt d0 = walk(p0);
         Dlt d1 = walk(p1);
+        if (stale) refresh();
         if (__any_sync(0xffffffffu, bot_on)) { sfc_override(p0, d0); sfc_override(p1, d1); }
         const bool cold = __all_sync(0xffffffffu, is_cold(t0, d0.ta) && is_cold(t1, d1.ta));
         const float e0 = thermo_e_pgw(cold, p0, t0, q0, d0.ta, d0.hur);
