@@ -56,6 +56,8 @@ struct TmaParams {
 };
 
 struct F4 { float x, y, z, w; };
+struct TagParked { static constexpr bool value = true; };
+struct TagStreamed { static constexpr bool value = false; };
 __device__ __forceinline__ F4 ldg4(const float4 *p) { const float4 v = __ldg(p); return F4{v.x, v.y, v.z, v.w}; }
 
 // NLEV_C / NP_C: number of levels and of parked levels as compile-time constants (0 = taken from the
@@ -510,11 +512,9 @@ pgw_column_tma_kernel(const __grid_constant__ pgw_timestep_args a, const __grid_
 
     // ---------------- the sweep: parked pairs, fixed point, streamed pairs ----------------
     float2 *pTe = st_Te + (size_t)(L - 1 - lst) * NT + tid;
-#pragma unroll 1
-    for (int j = 0; j <= npairs; ++j) {
-        const bool parked = j < np1;
-        if (j == np1) fixed_point();                  // np1 <= npairs: exactly once
-        if (j == npairs) break;
+    // one level pair; `parked` is a compile-time tag so that each of the two loops below gets its own body
+    auto pair_body = [&](const int j, auto parked_c) {
+        constexpr bool parked = decltype(parked_c)::value;
         const int l = max(L - 1 - 2 * j, 1);          // last pair of an odd column: levels (1, 0) again
         float2 mm0, mm1;
         if (parked) { mm0 = s_m[l]; mm1 = s_m[l - 1]; } else { mm0 = tp.m[l]; mm1 = tp.m[l - 1]; }
@@ -548,7 +548,21 @@ pgw_column_tma_kernel(const __grid_constant__ pgw_timestep_args a, const __grid_
             fence_proxy_async();
             mbar_arrive(bar_done + (j % kTmaSlots));
         }
+    };
+#ifdef PGW_TMA_ONE_LOOP
+#pragma unroll 1
+    for (int j = 0; j <= npairs; ++j) {
+        if (j == np1) fixed_point();                  // np1 <= npairs: exactly once
+        if (j == npairs) break;
+        if (j < np1) pair_body(j, TagParked{}); else pair_body(j, TagStreamed{});
     }
+#else
+#pragma unroll 1
+    for (int j = 0; j < np1; ++j) pair_body(j, TagParked{});
+    fixed_point();
+#pragma unroll 1
+    for (int j = np1; j < npairs; ++j) pair_body(j, TagStreamed{});
+#endif
 
     // ---------------- bookkeeping for the host-side checks ----------------
     const float2 m_top = tp.m[0];
