@@ -164,6 +164,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "PGW_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 #endif
 }
+// non-blocking probe of a phase (acquire): lets independent work sit between the probe and the branch on it
+__device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
 #ifndef PGW_PRODUCER_SLEEP_NS
 #define PGW_PRODUCER_SLEEP_NS 64
 #endif

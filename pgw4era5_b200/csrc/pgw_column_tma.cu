@@ -519,13 +519,15 @@ pgw_column_tma_kernel(const __grid_constant__ pgw_timestep_args a, const __grid_
         float2 mm0, mm1;
         if (parked) { mm0 = s_m[l]; mm1 = s_m[l - 1]; } else { mm0 = tp.m[l]; mm1 = tp.m[l - 1]; }
         float *const sl = ring + (j % kTmaSlots) * 8 * NT + tid;
-        mbar_wait(bar_full + (j % kTmaSlots), (j / kTmaSlots) & 1);
-        const float t0 = sl[NT], q0 = sl[3 * NT], u0 = sl[5 * NT], v0 = sl[7 * NT];    // row 1: level l
-        const float t1 = sl[0], q1 = sl[2 * NT], u1 = sl[4 * NT], v1 = sl[6 * NT];     // row 0: level l-1
+        // the walks need no slot data: they cover the round trip of the barrier probe (~100 cycles)
+        const bool ready = mbar_test(bar_full + (j % kTmaSlots), (j / kTmaSlots) & 1);
         const float p0 = fmaf(ps_f, mm0.y, mm0.x), p1 = fmaf(ps_f, mm1.y, mm1.x);
         Dlt d0 = walk(p0);
         Dlt d1 = walk(p1);
         if (stale) refresh();
+        if (!ready) mbar_wait(bar_full + (j % kTmaSlots), (j / kTmaSlots) & 1);
+        const float t0 = sl[NT], q0 = sl[3 * NT], u0 = sl[5 * NT], v0 = sl[7 * NT];    // row 1: level l
+        const float t1 = sl[0], q1 = sl[2 * NT], u1 = sl[4 * NT], v1 = sl[6 * NT];     // row 0: level l-1
         if (__any_sync(0xffffffffu, bot_on)) { sfc_override(p0, d0); sfc_override(p1, d1); }
         const bool cold = __all_sync(0xffffffffu, is_cold(t0, d0.ta) && is_cold(t1, d1.ta));
         const float e0 = thermo_e_pgw(cold, p0, t0, q0, d0.ta, d0.hur);
