@@ -56,10 +56,17 @@ shared-log walkers) -> 2.6 (fp32 stash, 3 CTAs/SM) -> 2.2 (batched prologue, nod
 1.99 (L2 node prefetch, iteration 0 folded into phase 1, consume-before-load walker steps) -> 1.69 (TMA pair ring with a
 producer warp, one float4 walker, one streaming loop: hot code 4 900 -> 600 SASS instructions, icache hit 94 -> 99.4 %%) ->
 1.63 (prefetch distances, incremental node offsets) -> 1.47 (fixed point through a polynomial in dps: the parked levels
-are integrated once, not once per iteration) -> 1.46 (Rd*Tv of the ERA state in float32, as the reference forms it).
-Measured and dropped afterwards: e-only stash (1.65 ms at 3 CTAs/SM, 2.15 at 4 with 96 registers), setmaxnreg with the
-5-warp CTA (hangs), L2 prefetch of the successor CTA's prologue (1.55 ms with or without the prefetch enabled: the
-extra code alone costs 6 %%; the kernel sits on the 128-register edge).
+are integrated once, not once per iteration) -> 1.46 (Rd*Tv of the ERA state in float32, as the reference forms it)
+-> 1.42 (next delta node kept blended in the walker state: 20 fewer moves per walker step) -> 1.376 (instance with
+compile-time level counts for L137 / 56 parked levels: loop bounds are immediates) -> 1.364 (walker refresh once per
+pair iteration: no false scoreboard dependency between lanes that cross a node at different levels) -> 1.287 (the sweep
+as two loops with a compile-time phase tag instead of one loop with run-time phase tests; 957 M -> 837 M warp
+instructions) -> 1.279 (non-blocking barrier probe before the walks).  Timings vary by ~1 %% between boxes; the bench box
+of this table ran under `sw_power_cap`.
+Measured and dropped: e-only stash (1.65 ms at 3 CTAs/SM, 2.15 at 4 with 96 registers), setmaxnreg with the 5-warp CTA
+(hangs), L2 prefetch of the successor CTA's prologue (+6 %% from the extra code alone at the time), suspend-time hints on
+the column warps' try_wait and longer producer back-off (no effect), a deeper ring for the streamed pairs in the dead
+stash (4/8/12 extra slots: 1.287/1.291/1.308 ms - the waits on `full` are the barrier round trip, not missing data).
 
 Tools: `summarize_ncu.py` (report -> markdown), `line_profile.py` (per-source-line instructions / stall samples, joins the
 ncu SASS page with `nvdisasm -g`), `gpu_cycle.sh` (tests + bench + capture in one `gpurun` call), `build_variant.sh`
