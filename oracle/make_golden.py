@@ -33,7 +33,7 @@ def import_reference_functions():
     return functions
 
 
-def main():
+def main(out_path=OUT):
     F = import_reference_functions()
     rng = np.random.default_rng(20240611)
     g = {}
@@ -114,8 +114,8 @@ def main():
     g["hum_esw"] = F.saturation_vapor_pressure_water_or_ice(pa, ta, water=True)
     g["hum_esi"] = F.saturation_vapor_pressure_water_or_ice(pa, ta, water=False)
 
-    np.savez_compressed(OUT, **g)
-    print("wrote", os.path.abspath(OUT), len(g), "arrays")
+    np.savez_compressed(out_path, **g)
+    print("wrote", os.path.abspath(out_path), len(g), "arrays")
 
 
 if __name__ == "__main__":

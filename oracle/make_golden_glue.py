@@ -120,7 +120,7 @@ def capture(fn, *a, **kw):
     return r, buf.getvalue()
 
 
-def main():
+def main(out=OUT):
     import warnings
     warnings.filterwarnings("ignore", message="no explicit representation of timezones")
     warnings.filterwarnings("ignore", category=DeprecationWarning)
@@ -335,8 +335,8 @@ def main():
         g["fd_in"] = raw
         g["fd_out"] = read_nc(os.path.join(tmp, "smooth.nc"))["ta"]
 
-    np.savez_compressed(OUT, **g)
-    print("wrote", OUT, len(g), "arrays", os.path.getsize(OUT), "bytes")
+    np.savez_compressed(out, **g)
+    print("wrote", out, len(g), "arrays", os.path.getsize(out), "bytes")
 
 
 if __name__ == "__main__":
