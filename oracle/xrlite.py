@@ -11,7 +11,7 @@ indexers, ``where``/``diff``/``expand_dims``/``transpose``/``concat``/``reindex`
 time/mask decoding in ``open_dataset`` -- so that ``oracle/make_golden_glue.py`` can execute the
 UNMODIFIED reference code from /root/reference and store what it returns as golden vectors
 (``tests/golden/reference_glue.npz``).  It is installed as ``sys.modules['xarray']`` by that script
-only; nothing in the product or in the tests imports it.
+only; the product never imports it, and ``tests/test_xrlite.py`` checks the semantics it claims.
 
 Deliberate limits: coordinates of operands are assumed to agree (xarray would inner-join; here a
 mismatch of an index coordinate raises), NetCDF-3 files only (scipy), standard calendars only.
