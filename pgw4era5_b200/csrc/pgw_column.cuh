@@ -9,7 +9,7 @@ namespace pgw {
 
 constexpr int kColumnThreads = 128;  // columns per CTA (= TMA box width)
 #ifndef PGW_NODE_L2_AHEAD
-#define PGW_NODE_L2_AHEAD 3
+#define PGW_NODE_L2_AHEAD 2
 #endif
 constexpr int kL2Ahead = PGW_NODE_L2_AHEAD;   // delta nodes pulled into L2 this many steps ahead of their use
 

@@ -44,6 +44,14 @@ constexpr int kTmaSlots = PGW_TMA_SLOTS;   // ring of level pairs, 4 KB each
 #define PGW_TMA_L2_AHEAD 0
 #endif
 constexpr int kTmaL2Ahead = PGW_TMA_L2_AHEAD;   // level pairs prefetched into L2 beyond the ones in the ring
+#ifndef PGW_TMA_UNROLL_PARKED
+#define PGW_TMA_UNROLL_PARKED 1
+#endif
+#ifndef PGW_TMA_UNROLL_STREAMED
+#define PGW_TMA_UNROLL_STREAMED 1
+#endif
+// unrolling either sweep loop costs more in instruction-cache misses than it saves (streamed x2: +4 %, x4: +13 %)
+constexpr int kUnrollParked = PGW_TMA_UNROLL_PARKED, kUnrollStreamed = PGW_TMA_UNROLL_STREAMED;
 constexpr double kTaylorMaxRel = 0.012;    // |ps_pgw - ps_era| / ps_era up to which the polynomial of the fixed point is used
 constexpr int kTmaMaxLev = 160;      // capacity of the parameter-space table of the upper levels
 
@@ -559,10 +567,10 @@ pgw_column_tma_kernel(const __grid_constant__ pgw_timestep_args a, const __grid_
         if (j < np1) pair_body(j, TagParked{}); else pair_body(j, TagStreamed{});
     }
 #else
-#pragma unroll 1
+#pragma unroll kUnrollParked
     for (int j = 0; j < np1; ++j) pair_body(j, TagParked{});
     fixed_point();
-#pragma unroll 1
+#pragma unroll kUnrollStreamed
     for (int j = np1; j < npairs; ++j) pair_body(j, TagStreamed{});
 #endif
 
