@@ -50,28 +50,39 @@ class _Reader:
         self.p += (n + 3) & ~3
         return s
 
-    def skip_values(self, nc_type, nelems):
-        self.p += ((_TYPES[nc_type][1] * nelems) + 3) & ~3
+    def values(self, nc_type, nelems):
+        """``nelems`` values of ``nc_type`` (padded to four bytes): str for NC_CHAR, else a native numpy
+        array, a python scalar if there is exactly one."""
+        dt, size = _TYPES[nc_type]
+        raw = bytes(self.b[self.p:self.p + size * nelems])
+        self.p += ((size * nelems) + 3) & ~3
+        if nc_type == 2:
+            return raw.rstrip(b"\x00").decode("utf-8", "replace")
+        a = np.frombuffer(raw, dtype=dt).astype(np.dtype(dt).newbyteorder("="))
+        return a.reshape(()).item() if a.size == 1 else a
 
     def att_list(self):
         tag = self.u32()
         n = self.size()
+        out = {}
         if tag == 0:
-            return
+            return out
         if tag != NC_ATTRIBUTE:
             raise NotNetCDF3("attribute list expected")
         for _ in range(n):
-            self.name()
+            name = self.name()
             t = self.u32()
-            self.skip_values(t, self.size())
+            out[name] = self.values(t, self.size())
+        return out
 
 
 class RawVar:
-    __slots__ = ("name", "dims", "shape", "nc_type", "dtype", "vsize", "begin", "is_record")
+    __slots__ = ("name", "dims", "shape", "nc_type", "dtype", "vsize", "begin", "is_record", "attrs")
 
-    def __init__(self, name, dims, shape, nc_type, vsize, begin, is_record):
+    def __init__(self, name, dims, shape, nc_type, vsize, begin, is_record, attrs=None):
         self.name, self.dims, self.shape, self.nc_type = name, dims, shape, nc_type
         self.dtype, self.vsize, self.begin, self.is_record = np.dtype(_TYPES[nc_type][0]), vsize, begin, is_record
+        self.attrs = dict(attrs or {})
 
     @property
     def record_shape(self):
@@ -117,7 +128,7 @@ class RawNC3:
                 dims.append((name, r.size()))
         elif tag != 0:
             raise NotNetCDF3("dimension list expected")
-        r.att_list()
+        self.attrs = r.att_list()
         tag, n = r.u32(), r.size()
         self.vars, rec_vars = {}, []
         if tag == NC_VARIABLE:
@@ -125,24 +136,23 @@ class RawNC3:
                 name = r.name()
                 nd = r.size()
                 dimids = [r.size() for _ in range(nd)]
-                r.att_list()
+                vattrs = r.att_list()
                 nc_type = r.u32()
                 vsize = r.size()
                 begin = r.u64() if version in (2, 5) else r.u32()
                 is_rec = nd > 0 and dims[dimids[0]][1] == 0
                 shape = tuple(dims[d][1] for d in dimids)
-                v = RawVar(name, tuple(dims[d][0] for d in dimids), shape, nc_type, vsize, begin, is_rec)
+                v = RawVar(name, tuple(dims[d][0] for d in dimids), shape, nc_type, vsize, begin, is_rec, vattrs)
                 self.vars[name] = v
                 if is_rec:
                     rec_vars.append(v)
         elif tag != 0:
             raise NotNetCDF3("variable list expected")
         self.version, self.header_size = version, r.p
-        # record size: sum of the (padded) vsizes; a single record variable is not padded
-        if len(rec_vars) == 1:
-            self.recsize = int(np.prod(rec_vars[0].shape[1:], dtype=np.int64)) * rec_vars[0].dtype.itemsize
-        else:
-            self.recsize = sum(v.vsize for v in rec_vars)
+        # record size: sum of the per-record sizes padded to four bytes (computed here: the 32-bit vsize of the
+        # header saturates for huge variables); a single record variable is not padded
+        per_rec = [int(np.prod(v.shape[1:], dtype=np.int64)) * v.dtype.itemsize for v in rec_vars]
+        self.recsize = per_rec[0] if len(rec_vars) == 1 else sum((b + 3) & ~3 for b in per_rec)
         if streaming:
             size = os.path.getsize(self.path)
             first = min((v.begin for v in rec_vars), default=size)
@@ -151,6 +161,21 @@ class RawNC3:
         self.dims = {name: (self.numrecs if length == 0 else length) for name, length in dims}
         for v in rec_vars:
             v.shape = (self.numrecs,) + v.shape[1:]
+
+    def read_variable(self, fobj, name):
+        """All values of ``name`` as a native-endian numpy array (record variables: every record).  Reads go
+        through ``preadv`` in pieces, so variables and records beyond 2 GiB are fine."""
+        v = self.vars[name]
+        out = np.empty(v.shape, dtype=v.dtype)
+        if v.is_record:
+            for rec in range(self.numrecs):
+                if out[rec:rec + 1].nbytes:
+                    self.read_into(fobj, name, out[rec:rec + 1], record=rec)
+        elif out.nbytes:
+            self.read_into(fobj, name, out)
+        if v.dtype.byteorder == ">":
+            return out.byteswap(inplace=True).view(v.dtype.newbyteorder("="))
+        return out
 
     def offset(self, name, record=0):
         v = self.vars[name]

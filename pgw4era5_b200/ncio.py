@@ -111,6 +111,19 @@ def open_dataset(path, decode_cf=False):
                 ds[name] = Variable(var.dimensions, np.array(var[...]), attrs)
             ds.attrs = {k: _scalar_attr(nc.getncattr(k)) for k in nc.ncattrs()}
         return ds
+    # NetCDF-3 (classic, 64-bit offset, CDF-5): own header parser + positional reads in pieces -- scipy's
+    # reader fails on records beyond 2 GiB (one global 0.25 degree ERA5 timestep is 2.3 GB)
+    from .nc3raw import NotNetCDF3, RawNC3
+    try:
+        raw = RawNC3(path)
+    except NotNetCDF3:
+        raw = None
+    if raw is not None:
+        with open(path, "rb", buffering=0) as f:
+            for name, v in raw.vars.items():
+                ds[name] = Variable(v.dims, raw.read_variable(f, name), v.attrs)
+        ds.attrs = dict(raw.attrs)
+        return ds
     from scipy.io import netcdf_file
     with netcdf_file(path, "r", mmap=False, maskandscale=False) as nc:
         for name, var in nc.variables.items():

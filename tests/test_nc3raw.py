@@ -112,3 +112,56 @@ def test_write_raw_assembles_the_output_file(tmp_path):
     ds3["RELHUM"] = ncio.Variable(("time", "level", "lat", "lon"), ds["T"].data)
     ds3.to_netcdf(str(tmp_path / "rh.nc"))
     assert S3._raw_layout(str(tmp_path / "rh.nc"), names, host_in) is None
+
+
+def test_open_dataset_matches_scipy_reader(tmp_path):
+    """ncio.open_dataset reads NetCDF-3 through nc3raw (no 2 GiB limit); same variables, values, dims and
+    attributes as scipy's reader on a file with record and fixed variables of several types."""
+    from scipy.io import netcdf_file
+    path = str(tmp_path / "mix.nc")
+    rng = np.random.default_rng(3)
+    with netcdf_file(path, "w", version=2) as f:
+        f.title, f.version_number = "mixed", np.float64(1.5)
+        f.createDimension("time", None); f.createDimension("lat", 3); f.createDimension("n", 5)
+        t = f.createVariable("time", "d", ("time",)); t[:] = [0.5, 1.5, 2.5]
+        t.units, t.calendar = "days since 2000-01-01 00:00:00", "standard"
+        a = f.createVariable("a", "f", ("time", "lat")); a[:] = rng.normal(size=(3, 3)).astype(np.float32)
+        a.scale = np.array([1.0, 2.0]); a.missing_value = np.float32(-999.0)
+        b = f.createVariable("b", "i", ("n",)); b[:] = np.arange(5, dtype=np.int32)
+        c = f.createVariable("c", "h", ("time",)); c[:] = np.array([7, 8, 9], dtype=np.int16)
+    got = ncio.open_dataset(path)
+    with netcdf_file(path, "r", mmap=False) as f:
+        assert set(got.keys()) == set(f.variables)
+        for name, v in f.variables.items():
+            want = np.array(v.data)
+            np.testing.assert_array_equal(got[name].data, want.astype(want.dtype.newbyteorder("=")), err_msg=name)
+            assert got[name].dims == v.dimensions and got[name].data.dtype.byteorder in "=|<"
+    assert got["time"].attrs["units"] == "days since 2000-01-01 00:00:00"
+    np.testing.assert_array_equal(got["a"].attrs["scale"], [1.0, 2.0])
+    assert got["a"].attrs["missing_value"] == -999.0 and got.attrs["title"] == "mixed" and got.attrs["version_number"] == 1.5
+
+
+def test_open_dataset_record_beyond_2gib(tmp_path):
+    """One global 0.25 degree timestep is a 2.3 GB record: scipy's reader gives up there, ours must not."""
+    import shutil
+    if shutil.disk_usage(str(tmp_path)).free < 6e9:
+        pytest.skip("not enough scratch space")
+    ds = ncio.Dataset()
+    ds["time"] = ncio.Variable(("time",), np.array([6.0]))
+    nl, ny, nx = 137, 721, 1440
+    x = np.zeros((1, nl, ny, nx), np.float32)
+    for k, name in enumerate(("T", "QV", "U", "V")):
+        x[0, k, 5, 7] = k + 1.0
+        ds[name] = ncio.Variable(("time", "level", "lat", "lon"), x.copy())
+        x[0, k, 5, 7] = 0.0
+    ds["PS"] = ncio.Variable(("time", "lat", "lon"), np.full((1, ny, nx), 1e5, np.float32))
+    path = str(tmp_path / "global.nc")
+    ds.to_netcdf(path)
+    assert os.path.getsize(path) > 2 ** 31
+    raw = RawNC3(path)
+    assert raw.recsize > 2 ** 31 and raw.numrecs == 1
+    back = ncio.open_dataset(path)
+    for k, name in enumerate(("T", "QV", "U", "V")):
+        assert back[name].data.shape == (1, nl, ny, nx) and back[name].data[0, k, 5, 7] == k + 1.0
+        assert float(back[name].data.sum()) == k + 1.0
+    assert back["PS"].data[0, 700, 1400] == np.float32(1e5)
