@@ -44,7 +44,7 @@ inputs cycling through 4 distinct device-resident timesteps (2.3 GB each >> 126 
 | step_02 smoothing, one 3-D daily variable | %(sm_ms).2f ms = %(sm_g).0f GB/s (%(sm_f).2f of peak) | `tests/bench_step02.py`, `r1_step02.json` |
 | step_02 regridding, one 3-D daily variable (28.8 GB out) | %(rg_ms).2f ms = %(rg_g).0f GB/s (%(rg_f).2f of peak) | same |
 | step_02 ocean variables (tos/siconc), 12 monthly fields, 170x360 curvilinear -> 721x1440, radius 1000 km | %(oc_ms).1f ms for the whole call (coordinate mapping, sort, Gaussian-kernel pass) | same |
-| file -> file, EU files (126 MB), NetCDF-3 | %(fp).1f files/s pipelined without host decoding (%(fst).1f steady state over 96 files) vs %(fd).1f with the scipy codec in the same pipeline vs %(fs).1f file by file | `tests/bench_files.py`, `r1_files.json` |
+| file -> file, EU files (126 MB), NetCDF-3 | %(fp).1f files/s pipelined without host decoding (%(fst).1f steady state over 96 files) vs %(fd).1f with the scipy codec in the same pipeline vs %(fs).1f file by file; global files (2.3 GB): %(fgl).2f files/s over 3 files | `tests/bench_files.py`, `r1_files.json` |
 | parity vs the executed reference (golden case, PS/FIS double) | ps %(p_ps).1e Pa, T %(p_t).1e K, QV %(p_q).1e; iterations identical for 4 settings | `tests/parity_report.py`, `r1_parity.json` |
 
 Launch list of one bench run (`r1_launches.csv`, ncu `--metrics gpu__time_duration.sum --clock-control none -k regex:pgw`;
@@ -82,7 +82,7 @@ ncu SASS page with `nvdisasm -g`), `gpu_cycle.sh` (tests + bench + capture in on
            rg_ms=step02["regridding"]["ms"], rg_g=step02["regridding"]["achieved_gbs"], rg_f=step02["regridding"]["frac_of_peak"],
            fp=files["pipelined_files_per_s"], fs=files["file_by_file_files_per_s"], launch=launch,
            fd=files["pipelined_decoding_files_per_s"], fst=files["steady_state_96_files"]["pipelined_files_per_s"],
-           oc_ms=step02["ocean_regridding"]["ms"], lb_ms=lb["ms_per_snapshot"], lb_it=lb["n_iter"], e2esteps=d["e2e"]["steps"],
+           oc_ms=step02["ocean_regridding"]["ms"], fgl=files["global_files"]["pipelined_files_per_s"], lb_ms=lb["ms_per_snapshot"], lb_it=lb["n_iter"], e2esteps=d["e2e"]["steps"],
            e2egb=d["e2e"]["value"] * d["e2e"]["h2d_bytes_per_step"] / 1e9,
            p_ps=par["vs_executed_reference"]["PS_FIS_double (default64)"]["PS"],
            p_t=par["vs_executed_reference"]["PS_FIS_double (default64)"]["T"],
