@@ -376,6 +376,33 @@ def test_fused_pass_matches_executed_reference(flavour, monkeypatch):
     _vs_reference(G, "tight64", res, tol)
 
 
+def test_tma_flavour_matches_executed_reference():
+    """The golden case has 30 columns, too few (and not a multiple of four) for the TMA flavour: tile it 32 times
+    along the longitude (columns are independent, the stopping rule is a maximum) and compare every tile with
+    what the reference wrote."""
+    G, era, deltas, when = _golden_case()
+    rep = 32
+    tile = lambda t: t.repeat(*([1] * (t.dim() - 1)), rep).contiguous()
+    era_t = {k: (tile(v) if isinstance(v, torch.Tensor) else v) for k, v in era.items()}
+    era_t["lon"] = np.arange(len(era["lon"]) * rep, dtype=np.float64)
+    deltas_t = {k: dict(v, data=tile(v["data"])) for k, v in deltas.items()}
+    eng = _engine(era_t, deltas_t)
+    res = eng.apply(_dev(era_t), when, ignore_top_pressure_error=True)
+    assert _uses_tma(eng, era_t) == 1
+    assert res["n_iter"] == int(G["pgw_default64_n_iter"])
+    np.testing.assert_allclose(res["phi_max_errors"], G["pgw_default64_errs"], rtol=0, atol=1e-3)
+    nx = len(era["lon"])
+    tol = dict(TOL)
+    tol.pop("delta_ps")
+    for name, t in tol.items():
+        g = res[name].detach().cpu().numpy().astype(np.float64)
+        r = G["pgw_default64_%s" % name].astype(np.float64).reshape(g.shape[:-1] + (nx,))
+        for k in (0, 13, rep - 1):
+            part = g[..., k * nx:(k + 1) * nx]
+            assert np.array_equal(np.isnan(part), np.isnan(r)), name
+            assert np.nanmax(np.abs(part - r)) <= t, (name, k, float(np.nanmax(np.abs(part - r))))
+
+
 @pytest.mark.parametrize("tag,name,value", [("pref_none64", "p_ref_inp", None), ("reinterp64", "i_reinterp", 1)])
 def test_staged_path_matches_executed_reference(tag, name, value):
     """The non-default settings (step_03:202-251, :330-343) through pgw4era5_b200.staged."""
