@@ -15,12 +15,15 @@
 //    further ahead are pulled into L2 with cp.async.bulk.prefetch.tensor.
 //
 // Per-thread global accesses are left only for the 2-D fields, the delta nodes and QV of the
-// parked levels.  The column threads execute one streaming loop for all 69 level pairs (the
-// fixed point runs inside it, between the last parked pair and the first streamed one), and ONE
-// delta walker serves all four variables: the packed float4 deltas (ta, hur, ua, va) share their
-// pressure nodes, and the surface node that replace_delta_sfc (functions.py:343-366) inserts into
-// the ta/hur columns only matters below the node under ps_hist, where it is applied as an override.
-// Both keep the hot code small: the previous version was instruction-cache bound.
+// parked levels.  The column threads run two loops over the 69 level pairs -- parked pairs, then the
+// fixed point, then streamed pairs -- generated from one body with a compile-time phase tag (a single
+// loop with run-time phase tests executes 12 % more instructions), and ONE delta walker serves all four
+// variables: the packed float4 deltas (ta, hur, ua, va) share their pressure nodes, and the surface node
+// that replace_delta_sfc (functions.py:343-366) inserts into the ta/hur columns only matters below the
+// node under ps_hist, where it is applied as an override.  The hot code stays small (an early version
+// with two walkers was instruction-cache bound; unrolling the loops costs more than it saves).
+// Per pair, the barrier probe is issued first, the two walks (which need no slot data) hide its round
+// trip; the walker's loads are issued once per pair iteration, a whole iteration before their first use.
 //
 // The fixed point does not re-integrate the parked levels in every iteration: their geopotential sum is
 // expanded once, during the sweep, as a polynomial in dps (see "the geopotential sums of the parked
