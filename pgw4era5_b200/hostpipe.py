@@ -11,6 +11,30 @@ import torch
 
 from . import _native as N
 
+def _pinned_write_combined(n_float):
+    """n_float float32 of page-locked, WRITE-COMBINED host memory (cudaHostAllocWriteCombined) as a torch
+    tensor, or None.  For H2D staging buffers only: the device reads them without snooping the CPU caches,
+    the CPU only ever writes them (reads from write-combined memory are very slow)."""
+    import ctypes
+    import glob
+    import os
+    try:
+        base = os.path.dirname(torch.__file__)
+        cand = glob.glob(os.path.join(base, "lib", "libcudart*.so*")) + \
+            glob.glob(os.path.join(os.path.dirname(base), "nvidia", "cuda_runtime", "lib", "libcudart.so*"))
+        rt = ctypes.CDLL(cand[0] if cand else "libcudart.so")
+        ptr = ctypes.c_void_p()
+        rt.cudaHostAlloc.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_size_t, ctypes.c_uint]
+        if rt.cudaHostAlloc(ctypes.byref(ptr), ctypes.c_size_t(4 * n_float), 0x04 | 0x01) != 0 or not ptr.value:
+            return None
+        buf = (ctypes.c_float * n_float).from_address(ptr.value)
+        t = torch.frombuffer(buf, dtype=torch.float32)
+        t._pgw_keep = (buf, rt)                      # never freed: lives as long as the process
+        return t
+    except Exception:
+        return None
+
+
 IN_FIELDS = ("PS", "FIS", "FR_LAND", "FR_SEA_ICE", "T_SKIN", "T_SO", "T", "QV", "U", "V")
 OUT_FIELDS = ("PS", "T_SKIN", "FR_SEA_ICE", "T_SO", "T", "QV", "U", "V", "delta_ps")
 
@@ -51,7 +75,10 @@ class HostPipeline:
         return out
 
     def alloc_host_inputs(self):
-        flat = torch.empty(self.n_in, dtype=torch.float32, pin_memory=True)
+        import os
+        flat = _pinned_write_combined(self.n_in) if os.environ.get("PGW_PINNED_WC") == "1" else None
+        if flat is None:
+            flat = torch.empty(self.n_in, dtype=torch.float32, pin_memory=True)
         return dict(flat=flat, **self._views(flat, self.in_levels))
 
     def alloc_host_outputs(self):
