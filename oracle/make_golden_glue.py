@@ -203,6 +203,24 @@ def main(out=OUT):
         g["ld_ts_full"] = F.load_delta(ddir, "ts", era_time, None).values
         g["ld_ts_clim"] = F.load_delta(ddir, "ts", era_time, None).mean(dim=["time"]).values
 
+        # ---- a DAILY delta series of a leap year (366 stamps): 29 February is dropped (:223-230), the other
+        # stamps are moved to the target's year (:235-238); dates next to the gap and at both year ends
+        ddir2 = os.path.join(tmp, "daily")
+        os.makedirs(ddir2)
+        stamps = np.datetime64("2000-01-01T12", "ns") + np.arange(366) * np.timedelta64(86400 * 10 ** 9, "ns")
+        daily = (np.arange(366, dtype=np.float32)[:, None, None] + rng.normal(size=(366, 2, 3)).astype(np.float32))
+        write_delta(os.path.join(ddir2, F.file_name_bases["SCEN-HIST"].format("tas")), "tas",
+                    dict(time=stamps, plev=None, data=daily), np.arange(2.0), np.arange(3.0))
+        ddates = [datetime(2006, 2, 28, 12), datetime(2006, 2, 28, 18), datetime(2006, 3, 1, 0), datetime(2006, 3, 1, 12),
+                  datetime(2006, 1, 1, 0), datetime(2006, 12, 31, 18), datetime(2008, 2, 29, 6), datetime(2006, 7, 4, 3)]
+        g["ldd_stamps"] = stamps.astype(np.int64)
+        g["ldd_data"] = daily
+        g["ldd_dates"] = np.array([d.isoformat() for d in ddates])
+        for i, d in enumerate(ddates):
+            r, _ = capture(F.load_delta, ddir2, "tas", era_time, d)
+            g["ldd_out_%d" % i] = r.values
+        g["ldd_full_len"] = np.array(F.load_delta(ddir2, "tas", era_time, None).shape[0])
+
         # ---- model-level pressure, vert_interp_delta / load_delta_interp (functions.py:306-431)
         akm = 0.5 * (era["ak"][1:] + era["ak"][:-1])
         bkm = 0.5 * (era["bk"][1:] + era["bk"][:-1])

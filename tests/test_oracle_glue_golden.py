@@ -153,3 +153,27 @@ def test_regrid_lat_lon():
 def test_filter_data():
     """functions.py:606-675 (the result is written back into the float32 array of the file)."""
     assert md(O.filter_data(G["fd_in"]), G["fd_out"]) <= 5e-7
+
+
+def test_daily_series_with_leap_day():
+    """load_delta on a 366-stamp daily series (functions.py:223-292): 29 February dropped, dates right next to
+    the gap, both year wraps, a leap-day target -- the oracle and the product's host-side bracket logic
+    (pgw4era5_b200/timeinterp.py, whose blend runs on the GPU) against the executed reference."""
+    from pgw4era5_b200 import timeinterp as TI
+    stamps = G["ldd_stamps"].astype("datetime64[ns]")
+    data = G["ldd_data"]
+    assert int(G["ldd_full_len"]) == 365
+    kept = TI.drop_leap_day(stamps)
+    assert len(kept) == 365 and 59 not in kept
+    delta = dict(time=stamps, data=data, plev=None)
+    for i, stamp in enumerate(G["ldd_dates"]):
+        when = datetime.fromisoformat(str(stamp))
+        want = G["ldd_out_%d" % i]
+        assert md(O.load_delta(delta, when), want) <= 1e-4, stamp
+        b = TI.bracket(stamps[kept], when)
+        lo, hi = data[kept][b.ind_before].astype(np.float64), data[kept][b.ind_after].astype(np.float64)
+        got = lo if b.exact else (hi - lo) / b.x_hi * b.x_new + lo
+        assert md(got[None], want) <= 1e-4, stamp
+    # 28 Feb 18:00 lies between 28 Feb 12:00 and 1 Mar 12:00: a quarter of the way across the dropped day
+    b = TI.bracket(stamps[kept], datetime(2006, 2, 28, 18))
+    assert (b.ind_before, b.ind_after) == (58, 59) and abs(b.x_new / b.x_hi - 0.25) < 1e-12
