@@ -586,6 +586,10 @@ def nan_ignoring_interp_arrays(land_fr, era5_lat, era5_lon, values, gcm_lat2d, g
         raise ValueError("latitude/longitude of the ocean grid must be 2-D like the data")   # see :940-943
     keep = ~torch.isnan(vals).all(dim=0)                   # points that are NaN in every field never count
     glat, glon, vals = glat[keep], glon[keep], vals[:, keep]
+    if glat.numel() == 0:                                  # no source point at all: everything is the null value
+        ny0, nx0 = np.size(_raw(era5_lat)), np.size(_raw(era5_lon))
+        full = torch.full((nt, ny0, nx0), float("nan"), device=vals.device, dtype=torch.float64)
+        return _back(full[0] if single else full, values)
     lat_m, lon_m, off = lonlat_to_meter(glon, glat, half_turn=True)
     # boundary points: the whole cloud once more to the west and to the east (:978-988)
     lat_bd = torch.cat([lat_m, lat_m, lat_m])
