@@ -147,3 +147,11 @@ def test_nan_ignoring_interp_gpu_matches_oracle(glob):
     one = F.nan_ignoring_interp_arrays(np.zeros((1, 1), np.float32), glat[5, 7:8], glon[5, 7:8] if glon[5, 7] <= 180 else glon[5, 7:8] - 360,
                                        np.where(np.isnan(vals[0]), 1.0, vals[0]), glat, glon, radius, 4.0)
     assert abs(float(one[0, 0]) - float(np.where(np.isnan(vals[0]), 1.0, vals[0])[5, 7])) < 1e-12
+
+
+@pytest.mark.gpu
+def test_all_nan_source_gives_all_nan():
+    from pgw4era5_b200 import functions as F
+    glat, glon, vals, tlat, tlon, land_fr, radius = _ocean_case(6, False)
+    out = F.nan_ignoring_interp_arrays(land_fr, tlat, tlon, np.full_like(vals, np.nan), glat, glon, radius, 4.0)
+    assert out.shape == (3, len(tlat), len(tlon)) and np.all(np.isnan(out))
