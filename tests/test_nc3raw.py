@@ -112,6 +112,23 @@ def test_write_raw_assembles_the_output_file(tmp_path):
     ds3["RELHUM"] = ncio.Variable(("time", "level", "lat", "lon"), ds["T"].data)
     ds3.to_netcdf(str(tmp_path / "rh.nc"))
     assert S3._raw_layout(str(tmp_path / "rh.nc"), names, host_in) is None
+    # two records in one file, a field of another size, a file that is not NetCDF-3, and the switch
+    ds4 = ncio.Dataset()
+    for k, v in ds.variables.items():
+        ds4[k] = ncio.Variable(v.dims, np.concatenate([v.data, v.data]), v.attrs) if v.dims[:1] == ("time",) else v
+    ds4.to_netcdf(str(tmp_path / "two.nc"))
+    assert RawNC3(str(tmp_path / "two.nc")).numrecs == 2
+    assert S3._raw_layout(str(tmp_path / "two.nc"), names, host_in) is None
+    small = dict(host_in, T=torch.empty((1, nl, ny, nx - 1), dtype=torch.float32))
+    assert S3._raw_layout(inp, names, small) is None
+    (tmp_path / "h5.nc").write_bytes(b"\x89HDF\r\n\x1a\n" + b"\0" * 64)
+    assert S3._raw_layout(str(tmp_path / "h5.nc"), names, host_in) is None
+    os.environ["PGW_RAW_IO"] = "0"
+    try:
+        assert S3._raw_layout(inp, names, host_in) is None
+    finally:
+        del os.environ["PGW_RAW_IO"]
+    assert S3._raw_layout(inp, names, host_in) is not None
 
 
 def test_open_dataset_matches_scipy_reader(tmp_path):
