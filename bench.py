@@ -55,10 +55,13 @@ class ClockSampler:
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index):
-        self.gpu, self.proc, self.t0, self.t1 = gpu_index, None, None, None
+    def __init__(self, gpu_indices):
+        """One nvidia-smi process for all the GPUs of the job, started by rank 0 only: a poller per rank (eight
+        of them on eight GPUs, each taking driver locks every 100 ms) disturbs the launch path it observes."""
+        self.gpu, self.proc, self.t0, self.t1 = gpu_indices, None, None, None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", ",".join(str(g) for g in gpu_indices),
+                                          "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
@@ -104,86 +107,88 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------- CPU arm
-def _cpu_sample(args):
-    """One bounded sample of the global workload on one host core: ny rows x 1440 columns."""
-    seed, ny, nx = args
+def _cpu_band(seed, j0, j1, ny=721, nx=1440):
+    """One task of the CPU arm: rows j0..j1 of a global 0.25 degree timestep through the oracle port of the
+    reference path, on one host core.  Returns (pid, seconds in the reference path, columns, n_iter); the
+    synthetic band is generated outside the timed part (it stands in for reading the file)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch
     torch.set_num_threads(1)
     from pgw4era5_b200 import synthetic as S
     from oracle import pgw_oracle as O
-    lat = np.linspace(-60.0, 60.0, ny)
-    era = S.make_era5(ny, nx, seed, lat=lat, lon=np.arange(nx) * 0.25)
+    lat = np.linspace(-90.0, 90.0, ny)[j0:j1]
+    era = S.make_era5(j1 - j0, nx, seed, lat=lat, lon=np.arange(nx) * (360.0 / nx))
     deltas = S.make_deltas(era, seed)
     e, d = S.to_numpy(era), S.to_numpy(deltas)
     t0 = time.perf_counter()
     out = O.pgw_for_era5(e, d, datetime(2006, 8, 2, 6), ignore_top_pressure_error=True)
-    return time.perf_counter() - t0, out["n_iter"]
+    return os.getpid(), time.perf_counter() - t0, (j1 - j0) * nx, out["n_iter"]
 
 
-def cpu_arm(n_tasks, procs, rows=8, nx=1440, pool=None):
-    """The oracle port of the reference path on `procs` host cores, one band per task, the
-    way parallel.IterMP spreads files over workers (parallel.py:18-32).  Returns
-    (timesteps/s, wall seconds, columns processed)."""
-    tasks = [(1000 + i, rows, nx) for i in range(n_tasks)]
-    t0 = time.perf_counter()
-    if pool is not None:
-        res = pool.map(_cpu_sample, tasks, chunksize=1)
-    else:
-        res = [_cpu_sample(t) for t in tasks]
-    wall = time.perf_counter() - t0
-    # time of the reference path only (the synthetic inputs are generated outside it): the slowest
-    # worker when every worker holds one band, the sum on one core
-    comp = [r[0] for r in res]
-    if pool is None:
-        wall = sum(comp)
-    elif n_tasks <= procs:
-        wall = max(comp)
-    cols = n_tasks * rows * nx
-    ts = cols / float(GRIDS["GL"][0] * GRIDS["GL"][1])
-    return ts / wall, wall, cols
+def cpu_arm(procs, rows_total, band_rows=8, seed0=1000):
+    """`rows_total` rows of the global grid (bands of `band_rows` x 1440 columns taken evenly from pole to pole),
+    one band per task, spread over `procs` worker processes by the package's IterMP -- the same interface and
+    the same one-task-per-file scheme as the reference's parallel.IterMP (parallel.py:36-68; /root/reference
+    itself does not exist on the GPU box).  The time of a step is the largest per-worker sum of the seconds
+    spent inside the reference path.  Returns (timesteps/s, seconds, columns)."""
+    from pgw4era5_b200.parallel import IterMP
+    ny = GRIDS["GL"][0]
+    nb = max(1, rows_total // band_rows)
+    starts = np.linspace(0, ny - band_rows, nb).astype(int)
+    step_args = [dict(seed=seed0 + i, j0=int(j), j1=int(j) + band_rows) for i, j in enumerate(starts)]
+    os.environ["PGW_ITERMP_NO_GPU"] = "1"           # CPU workers: no CUDA context per process
+    try:
+        pool = IterMP(njobs=procs, run_async=True, start_method="fork", quiet=True)
+        pool.run(_cpu_band, fargs={}, step_args=step_args)
+    finally:
+        os.environ.pop("PGW_ITERMP_NO_GPU", None)
+    per_pid = {}
+    for pid, sec, cols, _ in pool.output:
+        per_pid[pid] = per_pid.get(pid, 0.0) + sec
+    wall = max(per_pid.values())
+    cols = sum(r[2] for r in pool.output)
+    return cols / float(GRIDS["GL"][0] * GRIDS["GL"][1]) / wall, wall, cols
+
+
+def _cpu_sample_text(procs, cols, wall):
+    return ("%d columns = %.3f of one global 721x1440x137 timestep per step, in bands of 8x1440 columns, one band "
+            "per task over %d worker processes driven by pgw4era5_b200.parallel.IterMP (the reference's "
+            "parallel.IterMP interface, parallel.py:36-68; /root/reference is absent on the GPU box); fp64 "
+            "oracle port of the reference path (numpy + C column loops; the verbatim reference needs xarray, "
+            "absent in this image); %.1f s per step" % (cols, cols / 1038240.0, procs, wall))
 
 
 def run_reference(a):
-    """--impl reference: the reference path's CPU implementation (oracle port; the verbatim
-    reference needs xarray which this image lacks) on all host cores."""
+    """--impl reference: the reference path's CPU implementation (oracle port) on all host cores."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import multiprocessing as mp
     from oracle import build as ob
     ob.build()
-    procs = max(1, os.cpu_count() or 1)
-    procs = min(procs, 64)
+    procs = min(max(1, os.cpu_count() or 1), 64)
     steps = max(1, a.steps)
-    ctx = mp.get_context("spawn")
-    vals, walls = [], []
-    with ctx.Pool(procs) as pool:
-        pool.map(_cpu_sample, [(1, 2, 64)] * procs, chunksize=1)     # start workers, imports
-        # bounded sample: bands of `rows` x 1440 columns per worker and step, sized so that the whole
-        # --steps/--warmup run stays within about three minutes (one calibration step with 2 rows)
-        t_cal = time.perf_counter()
-        cpu_arm(procs, procs, 2, pool=pool)
-        t_cal = time.perf_counter() - t_cal
-        rows = int(max(1, min(8, 2 * 180.0 / (t_cal * (steps + max(a.warmup, 0))))))
-        for _ in range(max(a.warmup, 0)):
-            cpu_arm(procs, procs, rows, pool=pool)
-        for _ in range(steps):
-            v, w, c = cpu_arm(procs, procs, rows, pool=pool)
+    # bounded sample: a calibration step of one band per worker sizes the rows per step so that the whole
+    # --steps/--warmup run stays within about three minutes; at most one whole global timestep per step
+    t_cal = time.perf_counter()
+    _, w_cal, c_cal = cpu_arm(procs, 8 * procs)
+    t_cal = time.perf_counter() - t_cal
+    budget = 120.0 / (steps + max(a.warmup, 0))
+    rows = int(8 * procs * max(1.0, (budget - 1.0) / max(t_cal, 1e-3)))
+    rows = max(8 * procs, min(rows // 8 * 8, 720))
+    vals, walls, cols = [], [], 0
+    for i in range(max(a.warmup, 0) + steps):
+        v, w, cols = cpu_arm(procs, rows, seed0=2000 + 100 * i)
+        if i >= max(a.warmup, 0):
             vals.append(v); walls.append(w)
     value = float(np.mean(vals))
-    frac = procs * rows * 1440 / 1038240.0
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "timesteps/s", "n_gpus": a.gpus,
         "steps": steps, "warmup": a.warmup, "ms_per_step": 1000.0 * float(np.mean(walls)),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "global 721x1440x137 single timestep, plev19 monthly deltas (BASELINE configs[1])"},
+        "config": {"workload": "global 721x1440x137 single timestep, plev19 monthly deltas (BASELINE configs[1])",
+                   "sampled_fraction_of_timestep": cols / 1038240.0},
         "cpu_baseline": {"value": value, "unit": "timesteps/s", "cores": procs, "kind": "port",
-                         "sample": "per step %d bands of %dx1440 columns (%d columns = %.4f of one global "
-                                   "timestep), fp64 oracle port of the reference path (numpy + C column "
-                                   "loops), one band per worker process like parallel.IterMP; the verbatim "
-                                   "reference needs xarray, absent in this image"
-                                   % (procs, rows, procs * rows * 1440, frac)},
+                         "sample": _cpu_sample_text(procs, cols, float(np.mean(walls)))},
         "e2e": {"value": value, "unit": "timesteps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -191,6 +196,104 @@ def run_reference(a):
 
 
 # --------------------------------------------------------------------------- GPU arm
+def bare_link_test(dev, nbytes, world, barrier, reps=3):
+    """Bare pinned-memory copies of the e2e step's sizes, H2D and D2H at the same time on two streams, on all
+    ranks at once: the bound the platform sets for the host-buffer pipeline.  Returns GB/s per direction of
+    this rank (bytes / time for one direction while the other runs)."""
+    import torch
+    n = nbytes // 4
+    h_in = torch.empty(n, dtype=torch.float32, pin_memory=True)
+    h_out = torch.empty(n, dtype=torch.float32, pin_memory=True)
+    d_in = torch.empty(n, device=dev, dtype=torch.float32)
+    d_out = torch.empty(n, device=dev, dtype=torch.float32)
+    h_in.zero_(); h_out.zero_()
+    s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
+    def both():
+        with torch.cuda.stream(s1):
+            d_in.copy_(h_in, non_blocking=True)
+        with torch.cuda.stream(s2):
+            h_out.copy_(d_out, non_blocking=True)
+    both()
+    torch.cuda.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        both()
+    torch.cuda.synchronize()
+    el = (time.perf_counter() - t0) / reps
+    del h_in, h_out, d_in, d_out
+    return nbytes / el / 1e9
+
+
+def latband_leg(a, dev, rank, world, barrier):
+    """Latitude-band mode on BASELINE configs[4]: ONE global snapshot (plev37 deltas, threshold 1e-3, the worst
+    case iteration count), rows split over the ranks.  The stopping rule is field-global, so every snapshot
+    costs one all-reduce (MAX over the packed status block) between the column kernel and finalize.  Snapshots
+    are submitted back to back without host synchronisation; parity: each band against the same rows of a
+    whole-grid run on this GPU (bit-identical fields and the same iteration count expected)."""
+    import torch
+    import torch.distributed as dist
+    from pgw4era5_b200 import parallel as P, settings, synthetic as S
+    from pgw4era5_b200.engine import DeltaSet, PGWEngine
+    ny, nx = GRIDS[a.grid]
+    old = settings.thresh_phi_ref_max_error
+    settings.thresh_phi_ref_max_error = 1e-3
+    try:
+        era = S.make_era5(ny, nx, 5, device=dev, orog_seed=5)
+        deltas = S.make_deltas(era, 5, plev=S.PLEV37, device=dev)
+        when = datetime(2006, 8, 2, 6)
+        whole = PGWEngine(era["ak"], era["bk"], DeltaSet(deltas, device=dev), soil1=era["soil1"])
+        ref = whole.apply(era, when, ignore_top_pressure_error=True)
+        r0, r1 = P.split_rows(ny, world)[rank]
+        sub = {k: (v[..., r0:r1, :].contiguous() if isinstance(v, torch.Tensor) and v.dim() >= 3 else v)
+               for k, v in era.items()}
+        subd = {k: dict(v, data=v["data"][..., r0:r1, :].contiguous()) for k, v in deltas.items()}
+        eng = PGWEngine(era["ak"], era["bk"], DeltaSet(subd, device=dev), soil1=era["soil1"],
+                        group=dist.group.WORLD)
+        nslot = 4
+        outs = [eng.alloc_outputs(r1 - r0, nx, len(era["soil1"])) for _ in range(nslot)]
+        res = eng.apply(sub, when, out=outs[0], ignore_top_pressure_error=True)
+        same = {}
+        for name in ("PS", "T", "QV", "U", "V", "T_SKIN"):
+            g, w = res[name], ref[name][..., r0:r1, :]
+            same[name] = float((g - w).abs().nan_to_num().max())
+        ok = torch.tensor([float(res["n_iter"] == ref["n_iter"]), -max(same.values())], device=dev, dtype=torch.float64)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        for i in range(3):
+            eng.apply(sub, when, out=outs[i % nslot], ignore_top_pressure_error=True)
+        n_snap = a.latband_snapshots
+        eng.kernel_events = []
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        pend = []
+        for i in range(n_snap):
+            pend.append(eng.submit(sub, when, out=outs[i % nslot], ignore_top_pressure_error=True, slot=i % nslot))
+            if len(pend) >= nslot:
+                pend.pop(0).result()
+        n_it = [p.result()["n_iter"] for p in pend]
+        e1.record()
+        torch.cuda.synchronize()
+        k_ms = float(np.mean([x.elapsed_time(y) for x, y in eng.kernel_events]))
+        eng.kernel_events = None
+        t = torch.tensor([e0.elapsed_time(e1) / n_snap, k_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t2 = t[1:]
+        t = t[:1]
+        return {"workload": "one global %dx%dx137 snapshot, plev37 deltas, threshold 1e-3 (BASELINE configs[4]), "
+                            "%d latitude bands" % (ny, nx, world),
+                "ms_per_snapshot": float(t.item()), "snapshots": n_snap, "n_iter": int(n_it[-1]),
+                "n_iter_whole_grid": int(ref["n_iter"]), "n_iter_identical_on_all_bands": bool(ok[0].item() == 1.0),
+                "band_vs_whole_grid_max_abs_diff": float(-ok[1].item()),
+                "ms_per_snapshot_band_kernels_only": float(t2.item()),
+                "collective": "1 all-reduce(MAX) of %d float64 per snapshot (NCCL)" % 100,
+                "what_remains": "NCCL latency of the one all-reduce plus its stream hand-over, serial with the band "
+                                "kernel of the same snapshot (ms_per_snapshot - band_kernels_only)"}
+    finally:
+        settings.thresh_phi_ref_max_error = old
+
+
 def run_ours(a):
     import torch
     import torch.distributed as dist
@@ -214,60 +317,74 @@ def run_ours(a):
     ncol = ny * nx
     plev = S.PLEV19
 
-    # ---- inputs: climatology generated on rank 0 and broadcast (the one collective of the path)
-    era0 = S.make_era5(ny, nx, 2, device=dev, orog_seed=2)
-    deltas = S.make_deltas(era0, 2 if rank == 0 else 99, plev=plev, device=dev)
-    ds = DeltaSet(deltas, device=dev)
-    del deltas
-    bcast_ms = None
-    if world > 1:
-        bcast_ms = P.broadcast_deltas(ds, src=0)
-    eng = PGWEngine(era0["ak"], era0["bk"], ds, soil1=era0["soil1"])
-    # ring members: same terrain as the climatology, different weather
-    ring = [era0] + [S.make_era5(ny, nx, 100 * (rank + 1) + i, device=dev, orog_seed=2)
-                     for i in range(1, a.ring)]
-    outs = [eng.alloc_outputs(ny, nx, len(era0["soil1"])) for _ in range(2)]
-    base = datetime(2006, 8, 1, 0)
-    when = lambda i: base + timedelta(hours=6 * ((i * world + rank) % 124))
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ---- inputs: climatology generated on rank 0 and broadcast (the one collective of the path)
+    era0 = S.make_era5(ny, nx, 2, device=dev, orog_seed=2)
+    deltas = S.make_deltas(era0, 2 if rank == 0 else 99, plev=plev, device=dev)
+    ds = DeltaSet(deltas, device=dev)
+    del deltas
+    bcast = None
+    if world > 1:
+        bcast = {}
+        P.broadcast_deltas(ds, src=0, info=bcast)
+        t = torch.tensor([bcast["ms"]], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        bcast["ms"] = float(t.item())
+        bcast["gb_per_s"] = bcast["bytes"] / bcast["ms"] / 1e6
+    eng = PGWEngine(era0["ak"], era0["bk"], ds, soil1=era0["soil1"])
+    # ring members: same terrain as the climatology, different weather
+    ring = [era0] + [S.make_era5(ny, nx, 100 * (rank + 1) + i, device=dev, orog_seed=2)
+                     for i in range(1, a.ring)]
+    nslot = max(2, a.inflight)
+    outs = [eng.alloc_outputs(ny, nx, len(era0["soil1"])) for _ in range(nslot)]
+    base = datetime(2006, 8, 1, 0)
+    when = lambda i: base + timedelta(hours=6 * ((i * world + rank) % 124))
+
+    def run_steps(n, collect=None):
+        """n timesteps, up to `nslot` in flight: the host checks the status of a timestep (iteration count,
+        error bits; may trigger a rerun) while the next ones are already queued behind it."""
+        pend = []
+        for i in range(n):
+            pend.append(eng.submit(ring[i % a.ring], when(i), out=outs[i % nslot], ignore_top_pressure_error=True,
+                                   slot=i % nslot))
+            if len(pend) >= nslot:
+                r = pend.pop(0).result()
+                if collect is not None:
+                    collect.append(r["n_iter"])
+        last = pend[-1]
+        for p in pend:
+            r = p.result()
+            if collect is not None:
+                collect.append(r["n_iter"])
+        return last
+
     # ---- warm-up
-    pend = None
-    for i in range(a.warmup):
-        p = eng.submit(ring[i % a.ring], when(i), out=outs[i % 2], ignore_top_pressure_error=True, slot=i % 2)
-        if pend is not None:
-            pend.result()
-        pend = p
-    if pend is not None:
-        pend.result()
+    run_steps(a.warmup)
     n_iters = []
 
     # ---- timed region: device-resident inputs -> device-resident outputs
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(list(range(world))) if rank == 0 else None
     eng.kernel_events = []
     launches0 = eng.stats["launches"]
     barrier()
-    sampler.mark_start()
+    if sampler:
+        sampler.mark_start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_host0 = time.perf_counter()
     ev0.record()
-    pend = None
-    for i in range(a.steps):
-        p = eng.submit(ring[i % a.ring], when(i), out=outs[i % 2], ignore_top_pressure_error=True, slot=i % 2)
-        if pend is not None:
-            n_iters.append(pend.result()["n_iter"])
-        pend = p
-    n_iters.append(pend.result()["n_iter"])
+    last = run_steps(a.steps, n_iters)
     ev1.record()
     import ctypes
     from pgw4era5_b200 import _native
-    kernel_name = ("pgw_column_tma_kernel" if _native.lib.pgw_timestep_uses_tma(ctypes.byref(pend.args)) == 1
+    kernel_name = ("pgw_column_tma_kernel" if _native.lib.pgw_timestep_uses_tma(ctypes.byref(last.args)) == 1
                    else "pgw_column_kernel")
     barrier()
-    sampler.mark_stop()
+    if sampler:
+        sampler.mark_stop()
     ms = ev0.elapsed_time(ev1)
     kernel_ms = [e0.elapsed_time(e1) for e0, e1 in eng.kernel_events]
     eng.kernel_events = None
@@ -277,6 +394,17 @@ def run_ours(a):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     value = world * a.steps / (ms / 1000.0)
+    # host time per submit: the same loop with nothing to wait for would take this long per step
+    t0 = time.perf_counter()
+    for i in range(50):
+        eng._fill_args(ring[i % a.ring], when(i), outs[i % nslot], None, i % nslot)
+    host_us_fill = (time.perf_counter() - t0) / 50 * 1e6
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    ps = [eng.submit(ring[i % a.ring], when(i), out=outs[i % nslot], ignore_top_pressure_error=True, slot=i % nslot)
+          for i in range(nslot)]
+    host_us_submit = (time.perf_counter() - t0) / nslot * 1e6
+    [p.result() for p in ps]
 
     # ---- end to end through the public API with HOST buffers (pinned), copies inside the timing
     e2e = None
@@ -299,36 +427,66 @@ def run_ours(a):
         t = torch.tensor([el], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * a.e2e_steps / float(t.item()), "unit": "timesteps/s",
-               "h2d_bytes_per_step": pipe.h2d_bytes, "d2h_bytes_per_step": pipe.d2h_bytes,
-               "steps": a.e2e_steps, "slots": ns}
+        e2e_val = world * a.e2e_steps / float(t.item())
+        h2d_b, d2h_b = pipe.h2d_bytes, pipe.d2h_bytes
+        del pipe, hin, houts
+        # the platform's bound for this pipeline: bare pinned copies of the same sizes, both directions at once,
+        # on all ranks at once
+        link = bare_link_test(dev, h2d_b, world, barrier)
+        t = torch.tensor([link], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        link = float(t.item())
+        per_rank_gbs = (e2e_val / world) * h2d_b / 1e9
+        e2e = {"value": e2e_val, "unit": "timesteps/s",
+               "h2d_bytes_per_step": h2d_b, "d2h_bytes_per_step": d2h_b,
+               "steps": a.e2e_steps, "slots": ns,
+               "link_bound": {"gb_per_s_per_direction_per_gpu": link,
+                              "timesteps_per_s": world * link * 1e9 / h2d_b,
+                              "how": "bare pinned H2D + D2H copies of the step's sizes, both directions at once on "
+                                     "two streams, all %d ranks at the same time (min over ranks)" % world},
+               "frac_of_link": per_rank_gbs / link if link else None}
 
     # ---- roofline of the dominant kernel (the fused column kernel)
     peak, peak_kind = measured_peak_gbs()
     abytes = algorithmic_bytes(ncol, 137, len(plev), len(era0["soil1"]))
     k_ms = float(np.mean(kernel_ms)) if kernel_ms else None
     achieved = abytes / (k_ms / 1000.0) / 1e9 if k_ms else None
-    traffic = None
+    traffic, traffic_source = None, None
     try:
         with open(os.path.join(ROOT, "profiles", "column_kernel_traffic.json")) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
+            tj = json.load(f)
+            traffic = tj.get("dram_bytes_per_launch")
+            traffic_source = ("ncu --set full capture of this kernel on another B200 of the pool (%s), not "
+                              "measured during this run" % tj.get("source", "profiles/"))
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                "traffic_source": traffic_source,
                 "kernel": kernel_name, "kernel_ms": k_ms, "algorithmic_bytes": abytes,
-                "peak_kind": peak_kind}
+                "peak_kind": peak_kind,
+                "frac_whole_step": abytes / (ms / a.steps / 1000.0) / 1e9 / peak}
 
-    # ---- CPU baseline on a bounded sample (rank 0, N = 1 only)
+    # ---- latitude-band mode (BASELINE configs[4]) where there is more than one GPU
+    latband = None
+    if world > 1 and a.grid == "GL" and not a.no_latband:
+        ring.clear()
+        outs.clear()
+        torch.cuda.empty_cache()
+        latband = latband_leg(a, dev, rank, world, barrier)
+
+    # ---- CPU baseline on a bounded sample (rank 0, N = 1 only): all host cores, IterMP-driven
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu:
         from oracle import build as ob
         ob.build()
-        _cpu_sample((1, 2, 64))
-        v, wall, cols = cpu_arm(12, 1, rows=8)
-        cpu = {"value": v, "unit": "timesteps/s", "cores": 1, "kind": "port",
-               "sample": "12 bands of 8x1440 columns (%d columns = %.4f of one global timestep), fp64 oracle "
-                         "port on 1 host core, %.1f s" % (cols, cols / 1038240.0, wall)}
+        procs = min(max(1, os.cpu_count() or 1), 64)
+        cpu_arm(procs, 8 * procs)                                   # start-up costs out of the way
+        rows = max(8 * procs, min(720, 8 * procs * 6))
+        v, wall, cols = cpu_arm(procs, rows)
+        cpu = {"value": v, "unit": "timesteps/s", "cores": procs, "kind": "port",
+               "sample": _cpu_sample_text(procs, cols, wall)}
 
     if rank == 0:
         line = {
@@ -343,10 +501,14 @@ def run_ours(a):
                        "grid": a.grid, "ring": a.ring,
                        "l2": "inputs cycle through %d distinct 2.3 GB timesteps (>> 126 MB L2)" % a.ring,
                        "parallelism": "timestep-sharded x%d" % world, "numa_node": numa,
+                       "timesteps_in_flight": nslot,
                        "n_iter": {"min": int(min(n_iters)), "max": int(max(n_iters)), "steps": len(n_iters)},
-                       "engine": dict(eng.stats), "broadcast_ms": bcast_ms},
+                       "engine": dict(eng.stats),
+                       "host_us_per_submit": host_us_submit, "host_us_fill_args": host_us_fill,
+                       "broadcast_ms": bcast["ms"] if bcast else None, "broadcast": bcast,
+                       "latband": latband},
             "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-            "clocks": sampler.summary(),
+            "clocks": sampler.summary() if sampler else None,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -364,6 +526,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=48)
     ap.add_argument("--e2e-slots", type=int, default=2, help="timesteps in flight in the host-buffer pipeline")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--inflight", type=int, default=4, help="timesteps queued before the host checks the oldest")
+    ap.add_argument("--no-latband", action="store_true")
+    ap.add_argument("--latband-snapshots", type=int, default=100)
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
     if a.impl == "reference":

@@ -27,7 +27,8 @@
 extern "C" {
 #endif
 
-#define PGW_B200_ABI_VERSION 5   /* 5: + pgw_abi_version, pgw_integ_geopot_f64_f32, pgw_byteswap32, pgw_geod_to_meter_f64, pgw_gauss_interp_f64 */
+#define PGW_B200_ABI_VERSION 6   /* 6: + pgw_timestep_status, pgw_timestep_run/_finish, PGW_FLAG_REF_DTYPES, first_k,
+                                       pgw_band_pack/_unpack, pgw_regrid_bilinear_band_f32 */
 
 /* host-side return codes */
 #define PGW_OK               0
@@ -55,6 +56,13 @@ extern "C" {
 /* pgw_timestep_args.flags */
 #define PGW_FLAG_DIRECT  1   /* take the cp.async flavour of the column kernel, which integrates every parked
                                 level in every iteration (the TMA flavour uses a polynomial in dps) */
+#define PGW_FLAG_REF_DTYPES 2 /* reproduce the dtypes the reference computes in when PS and FIS are float32 in the
+                                ERA5 file (every real file): delta_ps and ps_pgw are float32
+                                (step_03_apply_to_era.py:186-195: zeros_like(PS), in-place +=), the half-level
+                                geopotential is a float32 running sum rounded on every level (functions.py:141,
+                                :147-152), -adj_factor*ps_pgw is a float32 product (step_03:302-303).  Implies
+                                PGW_FLAG_DIRECT.  Without the flag the accumulation is float64, i.e. the reference
+                                on a file that stores PS and FIS as double. */
 
 #define PGW_MAX_SOIL   16
 #define PGW_MAX_ITER   64
@@ -247,6 +255,12 @@ typedef struct pgw_timestep_args {
     uint64_t *maxerr;       /* [PGW_MAX_ITER] float64 bits, zeroed by the call */
     float *stats;           /* [2]: min target p, min source p (ta/hur)        */
     uint32_t *err;          /* sticky error word                               */
+    int32_t *first_k;       /* [2] or NULL: first iteration (0-based) in which PGW_ERR_PREF_BELOW_SFC /
+                               PGW_ERR_PS_BOUND fired (atomicMin; INT32_MAX = never).  The kernel runs k_spec
+                               iterations for every column, the reference stops after N: a condition that only
+                               fires in an iteration >= N never happened in the reference. */
+    uint32_t *poly_fallback; /* or NULL: number of (warp, iteration) pairs of the TMA flavour that left the range
+                               of the dps polynomial and integrated all parked levels directly (diagnostic) */
 } pgw_timestep_args;
 
 /* bytes of dynamic shared memory the column kernel needs for these args, or
@@ -268,6 +282,34 @@ typedef struct pgw_timestep_result {
 
 int pgw_timestep_finalize(const pgw_timestep_args *a, pgw_timestep_result *result_dev,
                           void *stream);
+
+/* The status block of one timestep in flight: what the kernels report and the host reads back.  maxerr, stats,
+ * err and first_k of the args must point at the members of ONE such block in device memory. */
+typedef struct pgw_timestep_status {
+    uint64_t maxerr[PGW_MAX_ITER];  /* max|phi error| per iteration, float64 bits                  */
+    pgw_timestep_result result;     /* written by finalize                                         */
+    float stats[2];                 /* min target pressure, min source pressure (functions.py:417) */
+    uint32_t err;                   /* PGW_ERR_* bits                                              */
+    int32_t first_k[2];             /* see pgw_timestep_args.first_k                               */
+    uint32_t poly_fallback;         /* see pgw_timestep_args.poly_fallback                         */
+} pgw_timestep_status;
+long long pgw_sizeof_timestep_status(void);
+
+/* One call per timestep: clears the status block, runs the column kernel and -- unless PGW_RUN_NO_FINALIZE --
+ * finalize, then copies the status block to `status_host` (pinned host memory, may be NULL) on the same stream.
+ * Latitude-band mode passes PGW_RUN_NO_FINALIZE, reduces the block over the bands (pgw_band_pack -> all-reduce MAX
+ * -> pgw_band_unpack) and calls pgw_timestep_finish (finalize + copy). */
+#define PGW_RUN_NO_FINALIZE 1
+int pgw_timestep_run(const pgw_timestep_args *a, pgw_timestep_status *status_dev,
+                     pgw_timestep_status *status_host, int run_flags, void *stream);
+int pgw_timestep_finish(const pgw_timestep_args *a, pgw_timestep_status *status_dev,
+                        pgw_timestep_status *status_host, void *stream);
+/* The status block as PGW_BAND_WORDS float64 such that an element-wise MAX over the latitude bands merges it:
+ * maxerr[64] | -stats[2] | one word per error bit [32] | -first_k[2]; and back.  The stopping rule of the
+ * reference is field-global (step_03_apply_to_era.py:189,308), so this is the one exchange of band mode. */
+#define PGW_BAND_WORDS (PGW_MAX_ITER + 2 + 32 + 2)
+int pgw_band_pack(const pgw_timestep_status *status_dev, double *words_dev, void *stream);
+int pgw_band_unpack(const double *words_dev, pgw_timestep_status *status_dev, void *stream);
 
 /* ------------------------------------------------------------------------
  * The staged per-timestep path: pgw_for_era5() run stage by stage on float64

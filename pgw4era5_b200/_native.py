@@ -26,6 +26,10 @@ ERR_PREF_BELOW_SFC = 1 << 5
 ERR_NO_PREF = 1 << 6
 ERR_PS_BOUND = 1 << 7
 FLAG_DIRECT = 1
+FLAG_REF_DTYPES = 2
+RUN_NO_FINALIZE = 1
+BAND_WORDS = 64 + 2 + 32 + 2
+INT32_MAX = 2 ** 31 - 1
 
 EXTRAP_MODES = {"off": 0, "linear": 1, "constant": 2, "nan": 3}
 
@@ -47,7 +51,7 @@ class TimestepArgs(C.Structure):
            ("p_ref", C.c_double), ("adj_factor", C.c_double),
            ("thresh_phi_ref_max_error", C.c_double), ("k_spec", C.c_int), ("ps_bound", C.c_double)]
         + [(n, c_fp) for n in ("PS_out", "T_SKIN_out", "FR_SEA_ICE_out", "T_SO_out", "T_out", "QV_out",
-                               "U_out", "V_out", "dps_out", "dps_traj", "maxerr", "stats", "err")]
+                               "U_out", "V_out", "dps_out", "dps_traj", "maxerr", "stats", "err", "first_k", "poly_fallback")]
     )
 
 
@@ -55,7 +59,13 @@ class TimestepResult(C.Structure):
     _fields_ = [("n_iter", C.c_int), ("converged", C.c_int), ("rewritten", C.c_int), ("reserved", C.c_int)]
 
 
-ABI_VERSION = 5          # PGW_B200_ABI_VERSION of include/pgw_b200.h
+class TimestepStatus(C.Structure):
+    """pgw_timestep_status: the device block the kernels report into and its pinned host copy."""
+    _fields_ = [("maxerr", C.c_uint64 * PGW_MAX_ITER), ("result", TimestepResult), ("stats", C.c_float * 2),
+                ("err", C.c_uint32), ("first_k", C.c_int32 * 2), ("poly_fallback", C.c_uint32)]
+
+
+ABI_VERSION = 6          # PGW_B200_ABI_VERSION of include/pgw_b200.h
 
 
 class NativeError(RuntimeError):
@@ -98,6 +108,11 @@ def _load():
         "pgw_timestep_uses_tma": (i, [C.POINTER(TimestepArgs)]),
         "pgw_timestep": (i, [C.POINTER(TimestepArgs), vp]),
         "pgw_timestep_finalize": (i, [C.POINTER(TimestepArgs), vp, vp]),
+        "pgw_sizeof_timestep_status": (ll, []),
+        "pgw_timestep_run": (i, [C.POINTER(TimestepArgs), vp, vp, i, vp]),
+        "pgw_timestep_finish": (i, [C.POINTER(TimestepArgs), vp, vp, vp]),
+        "pgw_band_pack": (i, [vp, vp, vp]),
+        "pgw_band_unpack": (i, [vp, vp, vp]),
         "pgw_zonal_mean_f32": (i, [vp, vp, ll, i, i, vp]),
         "pgw_regrid_bilinear_f32": (i, [vp, vp, vp, ll, i, i, i, i, vp, vp, vp, vp, vp, vp, vp]),
         "pgw_smooth_harmonic_f32": (i, [vp, vp, i, ll, vp]),
@@ -121,6 +136,9 @@ def _load():
     if lib.pgw_sizeof_timestep_args() != C.sizeof(TimestepArgs):
         raise ImportError("pgw_timestep_args layout mismatch: C %d vs ctypes %d"
                           % (lib.pgw_sizeof_timestep_args(), C.sizeof(TimestepArgs)))
+    if lib.pgw_sizeof_timestep_status() != C.sizeof(TimestepStatus):
+        raise ImportError("pgw_timestep_status layout mismatch: C %d vs ctypes %d"
+                          % (lib.pgw_sizeof_timestep_status(), C.sizeof(TimestepStatus)))
     return lib, sorted(sig)
 
 

@@ -2,6 +2,7 @@
 // (pgw_timestep.cu: per-thread cp.async flavour, pgw_column_tma.cu: TMA flavour).
 #pragma once
 #include <cuda.h>
+#include <limits.h>
 
 #include "pgw_common.cuh"
 
@@ -77,6 +78,23 @@ __device__ __forceinline__ double ln_ratio(double pb, double pt, const LnConst &
     const double s2 = s * s;
     double poly = fma(s2, k.c7, k.c5);
     poly = fma(s2, poly, k.c3);
+    poly = fma(s2, poly, 2.0);
+    return s * poly;
+}
+
+// PGW_FLAG_REF_DTYPES: ln(pb) - ln(pt) the way numpy forms it (functions.py:136-138: the difference of two float64
+// logs, each within an ulp of ln p ~ 11.5, i.e. an absolute error of ~2e-15) to that same accuracy: exact
+// division, series to s^10 (relative truncation error s^12/13 < 2e-16 for s < 0.06), the exact logs otherwise.
+// The value is then rounded into a float32 running sum (ulp 0.0078 m2/s2), so what matters is that it sits
+// within ~1e-10 m2/s2 of numpy's: a different rounding of the sum then happens once in ~1e7 levels.
+__device__ __forceinline__ double ln_ratio_ref(double pb, double pt) {
+    const double s = (pb - pt) / (pb + pt);
+    if (!(fabs(s) < 0.06)) return log(pb) - log(pt);
+    const double s2 = s * s;
+    double poly = fma(s2, 2.0 / 11.0, 2.0 / 9.0);
+    poly = fma(s2, poly, 2.0 / 7.0);
+    poly = fma(s2, poly, 2.0 / 5.0);
+    poly = fma(s2, poly, 2.0 / 3.0);
     poly = fma(s2, poly, 2.0);
     return s * poly;
 }
@@ -222,6 +240,7 @@ __device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wai
 
 // ---- host-side pieces shared by pgw_timestep.cu and pgw_column_tma.cu
 struct pgw_column_plan {
+    bool ref;           // PGW_FLAG_REF_DTYPES
     bool tma;
     int lst, np;        // top level of the stash, number of parked levels
     size_t smem;
@@ -230,3 +249,6 @@ struct pgw_column_plan {
 // pgw_column_tma.cu
 bool pgw_tma_eligible(const pgw_timestep_args *a, int lst_generic, int *lst_tma, size_t *smem);
 int pgw_launch_column_tma(const pgw_timestep_args *a, const pgw_column_plan &plan, cudaStream_t st);
+// Opt a kernel in to `smem` bytes of dynamic shared memory on the CURRENT device.  The attribute is per device
+// and per kernel; `slot` (0..15) names the kernel variant in a per-device table of what has been configured.
+int pgw_ensure_smem(const void *kernel, int slot, size_t smem, int np);

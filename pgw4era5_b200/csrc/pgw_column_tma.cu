@@ -167,6 +167,7 @@ pgw_column_tma_kernel(const __grid_constant__ pgw_timestep_args a, const __grid_
     const uint32_t c = (c_raw >= n) ? n - 1 : c_raw;
     const bool valid = c_raw < n;
     unsigned errbits = 0;
+    int k_pref = INT32_MAX, k_bound = INT32_MAX;     // first iteration in which the two ps-dependent checks fired
 
     // ---------------- surface, skin and soil (step_03:103-146) ----------------
     const float ps_f = __ldg(a.PS + c);
@@ -352,7 +353,7 @@ pgw_column_tma_kernel(const __grid_constant__ pgw_timestep_args a, const __grid_
     double pb_era = fma(PSd, hl_sfc.y, hl_sfc.x);
     double acc_era = 0.0;
     bool era_open = pb_era >= pref;                 // still below p_ref
-    if (!era_open) errbits |= PGW_ERR_PREF_BELOW_SFC;
+    if (!era_open) { errbits |= PGW_ERR_PREF_BELOW_SFC; k_pref = 0; }
     float psn_f = ps_f;                             // ps used for QV; replaced after the iteration
 
     // ---------------- the geopotential sums of the parked levels ----------------
@@ -453,9 +454,9 @@ pgw_column_tma_kernel(const __grid_constant__ pgw_timestep_args a, const __grid_
             psn = PSd + dps;
             psn_f = (float)psn;
             if (valid) *traj = (float)dps;
-            if (psn > a.ps_bound) errbits |= PGW_ERR_PS_BOUND;
+            if (psn > a.ps_bound) { errbits |= PGW_ERR_PS_BOUND; k_bound = min(k_bound, k); }
             double pb = fma(psn, hl_sfc.y, hl_sfc.x);
-            if (pb < pref) errbits |= PGW_ERR_PREF_BELOW_SFC;
+            if (pb < pref) { errbits |= PGW_ERR_PREF_BELOW_SFC; k_pref = min(k_pref, k); }
             // Tv = T (1 + 0.61 hus), hus = 0.622 e / (p - 0.378 e)   (functions.py:66-72, :144)
             auto layer = [&](int l, const float2 te, double pt_or_ref, double acc_in) {
                 const float2 m = s_m[l];
@@ -485,6 +486,7 @@ pgw_column_tma_kernel(const __grid_constant__ pgw_timestep_args a, const __grid_
                     if (part) break;
                 }
             } else {
+                if ((tid & 31) == 0 && a.poly_fallback) atomicAdd(a.poly_fallback, 1u);
                 // layers ltop..L-1 are entirely below p_ref for this ps; it moves by at most a level or two
                 while (ltop > lst) { const double2 h = s_hl[ltop - 1]; if (fma(psn, h.y, h.x) >= pref) --ltop; else break; }
                 while (ltop < L) { const double2 h = s_hl[ltop]; if (fma(psn, h.y, h.x) < pref) ++ltop; else break; }
@@ -586,7 +588,13 @@ pgw_column_tma_kernel(const __grid_constant__ pgw_timestep_args a, const __grid_
         atomicMin(reinterpret_cast<unsigned *>(a.stats), __float_as_uint(fmaxf(p_top, 0.0f)));
         atomicMin(reinterpret_cast<unsigned *>(a.stats) + 1, __float_as_uint(fmaxf(min_src_p, 0.0f)));
     }
-    if (errbits && valid) atomicOr(a.err, errbits);
+    if (errbits && valid) {
+        atomicOr(a.err, errbits);
+        if (a.first_k) {
+            if (k_pref != INT32_MAX) atomicMin(a.first_k, k_pref);
+            if (k_bound != INT32_MAX) atomicMin(a.first_k + 1, k_bound);
+        }
+    }
 }
 
 }  // namespace pgw
@@ -629,7 +637,28 @@ EncodeTiledFn encode_tiled() {
 
 bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// Encoded maps are remembered per (base address, ncol, nlev): a pipeline cycles through a handful of input and
+// output buffers, and eight driver calls per launch were a visible part of the host time per timestep.
+struct MapCacheEntry { const float *base; long long ncol; int nlev; CUtensorMap map; };
+constexpr int kMapCache = 128;
+
+int encode_map(CUtensorMap *m, const float *base, long long ncol, int nlev);
+
 int make_map(CUtensorMap *m, const float *base, long long ncol, int nlev) {
+    static thread_local MapCacheEntry cache[kMapCache];
+    static thread_local int used = 0, next = 0;
+    for (int i = 0; i < used; ++i)
+        if (cache[i].base == base && cache[i].ncol == ncol && cache[i].nlev == nlev) { *m = cache[i].map; return PGW_OK; }
+    const int rc = encode_map(m, base, ncol, nlev);
+    if (rc != PGW_OK) return rc;
+    MapCacheEntry &e = cache[next];
+    e.base = base; e.ncol = ncol; e.nlev = nlev; e.map = *m;
+    next = (next + 1) % kMapCache;
+    if (used < kMapCache) ++used;
+    return PGW_OK;
+}
+
+int encode_map(CUtensorMap *m, const float *base, long long ncol, int nlev) {
     const cuuint64_t dims[2] = {(cuuint64_t)ncol, (cuuint64_t)nlev};
     const cuuint64_t strides[1] = {(cuuint64_t)ncol * sizeof(float)};
     const cuuint32_t box[2] = {(cuuint32_t)kColumnThreads, 2u};
@@ -674,22 +703,8 @@ int pgw_launch_column_tma(const pgw_timestep_args *a, const pgw_column_plan &pla
     const bool l137 = a->nlev == 137 && plan.np == 56 && plan.lst == 137 - 56;
     auto kern = plan.fast ? (l137 ? pgw::pgw_column_tma_kernel<true, 137, 56> : pgw::pgw_column_tma_kernel<true, 0, 0>)
                           : (l137 ? pgw::pgw_column_tma_kernel<false, 137, 56> : pgw::pgw_column_tma_kernel<false, 0, 0>);
-    static thread_local size_t configured[4] = {0, 0, 0, 0};
-    size_t &conf = configured[(plan.fast ? 1 : 0) + (l137 ? 2 : 0)];
-    if (plan.smem > conf) {
-        int dev = 0, max_optin = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-        if (plan.smem > (size_t)max_optin) {
-            pgw_set_error("column stash needs %zu B of shared memory (%d levels below p_ref), device allows %d",
-                          plan.smem, plan.np, max_optin);
-            return PGW_E_SMEM;
-        }
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem) != cudaSuccess)
-            return pgw_check_launch("cudaFuncSetAttribute");
-        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        conf = plan.smem;
-    }
+    if ((rc = pgw_ensure_smem((const void *)kern, 4 + (plan.fast ? 1 : 0) + (l137 ? 2 : 0), plan.smem, plan.np)) != PGW_OK)
+        return rc;
     const unsigned grid = (unsigned)((a->ncol + kColumnThreads - 1) / kColumnThreads);
     kern<<<grid, kColumnThreads + 32, plan.smem, st>>>(*a, tp, plan.lst, plan.np);
     return pgw_check_launch("pgw_column_tma_kernel");

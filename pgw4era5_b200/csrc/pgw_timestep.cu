@@ -41,8 +41,11 @@ struct Walk2 {
 
 constexpr int kRing = 5;     // levels in flight per thread (cp.async ring, +1 spare slot)
 
-template <int NT, bool FAST>
-__global__ void __launch_bounds__(NT, 3)
+// REF: the dtypes the reference computes in on a file with float32 PS and FIS (PGW_FLAG_REF_DTYPES): float32
+// delta_ps / ps_pgw, the half-level geopotential as a float32 running sum that is rounded on every level, for the
+// ERA state and for the PGW state of every iteration, pressures as the two rounded operations ak + ps*bk.
+template <int NT, bool FAST, bool REF>
+__global__ void __launch_bounds__(NT, REF ? 2 : 3)
 pgw_column_kernel(const __grid_constant__ pgw_timestep_args a, const int lst, const int np) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int L = a.nlev, K = a.nplev;
@@ -54,6 +57,7 @@ pgw_column_kernel(const __grid_constant__ pgw_timestep_args a, const int lst, co
     float *s_plev = reinterpret_cast<float *>(s_m + L);                 // [K] ascending
     float *s_inv_plev = s_plev + K;                                     // [K]
     float *s_inv_w = s_inv_plev + K;                                    // [K] 1/log2(p[j+1]/p[j])
+    float *st_r = s_inv_w + K;                                          // REF: [np][NT] (T_era + dta) - fp32 T_pgw
 
     const int tid = threadIdx.x;
     for (int i = tid; i <= L; i += NT) s_hl[i] = make_double2(a.ak[i], a.bk[i]);
@@ -76,6 +80,7 @@ pgw_column_kernel(const __grid_constant__ pgw_timestep_args a, const int lst, co
     // same values to the same addresses, which keeps the whole kernel free of tail branches.
     if (c >= n) c = n - 1;
     unsigned errbits = 0;
+    int k_pref = INT32_MAX, k_bound = INT32_MAX;     // first iteration in which the two ps-dependent checks fired
 
     // ---- async ring: this thread's T, QV, U, V of one level per slot
     const float *gT = a.T, *gQ = a.QV, *gU = a.U, *gV = a.V;
@@ -235,8 +240,12 @@ pgw_column_kernel(const __grid_constant__ pgw_timestep_args a, const int lst, co
     double pb_era = fma(PSd, hl_sfc.y, hl_sfc.x);
     double acc_era = 0.0;
     bool era_open = pb_era >= pref;                 // still below p_ref
-    if (!era_open) errbits |= PGW_ERR_PREF_BELOW_SFC;
+    if (!era_open) { errbits |= PGW_ERR_PREF_BELOW_SFC; k_pref = 0; }
     float psn_f = ps_f;                             // ps used for QV; replaced after the iteration
+    // REF: ak + ps*bk as numpy evaluates it (two rounded operations, step_03:64-66, :196-199)
+    auto hyb = [](double ps, double2 h) { return __dadd_rn(h.x, __dmul_rn(ps, h.y)); };
+    float phi32_era = r_fis;                        // REF: float32 half-level geopotential of the ERA state
+    double phi_ref_era = 0.0;
 
     const auto read_fence = [](float x0, float x1, float x2, float x3) { return reg_fence(x0, x1, x2, x3); };
     // The per-level work is split into the (sequential, cheap) walker step and the (independent,
@@ -272,7 +281,24 @@ pgw_column_kernel(const __grid_constant__ pgw_timestep_args a, const int lst, co
         // ERA geopotential of one layer (functions.py:128-189), sequential in the column
         // The first iteration of the fixed point (dps = 0) integrates the PGW state over the
         // same pressures, so its sum is taken here as well and phase 2 starts at iteration 1.
+        float *pTr = st_r + (size_t)(L - 1 - lst) * NT + tid;
         auto era_layer = [&](int l, float p, float t, float q, float dta, float t_pgw, float e_pgw) {
+            if constexpr (REF) {
+                const double tpd = (double)t_pgw;
+                pTr[-(L - 1 - l) * NT] = (float)(((double)t + (double)dta) - tpd);
+                if (era_open) {
+                    const double Pt = hyb(PSd, s_hl[l]);
+                    const double rtv = rd_tv(t, q);                  // CON_RD * tav, float32 products (:144, :151)
+                    if (Pt < pref) {                                 // functions.py:174-179, float64
+                        phi_ref_era = (double)phi32_era + rtv * ln_ratio_ref(pb_era, pref);
+                        era_open = false;
+                    } else {                                         // functions.py:147-152, stored as float32
+                        phi32_era = (float)((double)phi32_era + rtv * ln_ratio_ref(pb_era, Pt));
+                        pb_era = Pt;
+                    }
+                }
+                return;
+            }
             if (era_open) {
                 const double2 hl = s_hl[l];
                 double pt = fma(PSd, hl.y, hl.x);
@@ -332,7 +358,7 @@ pgw_column_kernel(const __grid_constant__ pgw_timestep_args a, const int lst, co
         }
     }
     const double fis = (double)r_fis;
-    const double phi_era = fis + acc_era;                            // acc_era holds Rd * Tv * dlnp
+    const double phi_era = REF ? phi_ref_era : fis + acc_era;        // acc_era holds Rd * Tv * dlnp
     const double gdzg = blend_f64(a.zg_ref, r_zg) * kG;              // step_03:292-295
     const float2 *const bTe = st_Te + (size_t)(L - 1 - lst) * NT + tid;  // lowest level of the stash
     const double t_low = t_low_d;                                 // ta_pgw on the lowest level
@@ -343,13 +369,56 @@ pgw_column_kernel(const __grid_constant__ pgw_timestep_args a, const int lst, co
     int ltop = lst + 1;                 // first layer (from the top) lying entirely below p_ref
     float *traj = a.dps_traj + c;
     for (int k = 0; k < a.k_spec; ++k, traj += n) {
-        dps += adj;
-        psn = PSd + dps;
-        psn_f = (float)psn;
+        if constexpr (REF) {
+            // delta_ps is float32 (zeros_like(PS)) and += keeps that; ps_pgw = PS + delta_ps is a float32 sum
+            // (step_03_apply_to_era.py:186-195)
+            const float dps32 = (float)(dps + adj);
+            dps = (double)dps32;
+            psn_f = __fadd_rn(ps_f, dps32);
+            psn = (double)psn_f;
+        } else {
+            dps += adj;
+            psn = PSd + dps;
+            psn_f = (float)psn;
+        }
         *traj = (float)dps;
-        if (psn > a.ps_bound) errbits |= PGW_ERR_PS_BOUND;
-        double pb = fma(psn, hl_sfc.y, hl_sfc.x);
-        if (pb < pref) errbits |= PGW_ERR_PREF_BELOW_SFC;
+        if (psn > a.ps_bound) { errbits |= PGW_ERR_PS_BOUND; k_bound = min(k_bound, k); }
+        double pb = REF ? hyb(psn, hl_sfc) : fma(psn, hl_sfc.y, hl_sfc.x);
+        if (pb < pref) { errbits |= PGW_ERR_PREF_BELOW_SFC; k_pref = min(k_pref, k); }
+        if constexpr (REF) {
+            // integ_geopot of the PGW state with the float32 half-level geopotential (functions.py:141-152)
+            float phi32 = r_fis;
+            double phi_pgw = 0.0;
+            bool open = true;
+            const float2 *pTe = bTe;
+            const float *pTr = st_r + (size_t)(L - 1 - lst) * NT + tid;
+            for (int l = L - 1; l >= lst; --l, pTe -= NT, pTr -= NT) {
+                const float2 m = s_m[l];
+                const float2 te = *pTe;
+                const double Td = (double)te.x + (double)*pTr;
+                const double Pt = hyb(psn, s_hl[l]);
+                const float g = fast_rcp(fmaf(-0.378f, te.y, fmaf(psn_f, m.y, m.x)));
+                const double rtv = kRd * (Td * (1.0 + (double)((0.61f * 0.622f) * te.y * g)));
+                if (Pt < pref) {
+                    phi_pgw = (double)phi32 + rtv * ln_ratio_ref(pb, pref);
+                    open = false;
+                    break;
+                }
+                phi32 = (float)((double)phi32 + rtv * ln_ratio_ref(pb, Pt));
+                pb = Pt;
+            }
+            if (open) { phi_pgw = (double)phi32; errbits |= PGW_ERR_PS_BOUND; k_bound = min(k_bound, k); }
+            const double err = (phi_pgw - phi_era) - gdzg;
+            // -adj_factor * ps_pgw is a float32 product (python scalar x float32 array, step_03:302-303)
+            const float aps = __fmul_rn((float)(-a.adj_factor), psn_f);
+            adj = (double)aps / (kRd * t_low) * err;
+            double ae = isnan(err) ? 0.0 : fabs(err);
+            ae = warp_max(ae);
+            if ((tid & 31) == 0 && ae > 0.0)
+                atomicMax(reinterpret_cast<unsigned long long *>(a.maxerr + k),
+                          (unsigned long long)__double_as_longlong(ae));
+            continue;
+        }
         double acc = acc_res;
         if (k == 0) {
             acc += acc_pgw0;            // psn == PS: summed in phase 1 together with the ERA state
@@ -455,13 +524,23 @@ pgw_column_kernel(const __grid_constant__ pgw_timestep_args a, const int lst, co
         atomicMin(reinterpret_cast<unsigned *>(a.stats), __float_as_uint(fmaxf(p_top, 0.0f)));
         atomicMin(reinterpret_cast<unsigned *>(a.stats) + 1, __float_as_uint(fmaxf(min_src_p, 0.0f)));
     }
-    if (errbits) atomicOr(a.err, errbits);
+    if (errbits) {
+        atomicOr(a.err, errbits);
+        if (a.first_k) {
+            if (k_pref != INT32_MAX) atomicMin(a.first_k, k_pref);
+            if (k_bound != INT32_MAX) atomicMin(a.first_k + 1, k_bound);
+        }
+    }
 }
 
-__global__ void pgw_timestep_init_kernel(uint64_t *maxerr, float *stats) {
+__global__ void pgw_timestep_init_kernel(uint64_t *maxerr, float *stats, uint32_t *err, int32_t *first_k,
+                                         uint32_t *poly_fallback) {
     const int i = threadIdx.x;
+    if (i == 0 && poly_fallback) *poly_fallback = 0u;
     if (i < PGW_MAX_ITER) maxerr[i] = 0ull;
     if (i < 2) stats[i] = INFINITY;
+    if (i < 2 && first_k) first_k[i] = INT32_MAX;
+    if (i == 0) *err = 0u;
 }
 
 // N = first k with max|err_k| <= thresh (step_03:189,308)
@@ -490,7 +569,8 @@ pgw_rewrite_kernel(const __grid_constant__ pgw_timestep_args a, const pgw_timest
     const double PSd = (double)a.PS[c];
     const double dps_n = (double)a.dps_traj[(long long)(N - 1) * n + c];
     const double dps_s = (double)a.dps_traj[(long long)(a.k_spec - 1) * n + c];
-    const double ps_n = PSd + dps_n, ps_s = PSd + dps_s;
+    double ps_n = PSd + dps_n, ps_s = PSd + dps_s;
+    if (a.flags & PGW_FLAG_REF_DTYPES) { ps_n = (double)(float)ps_n; ps_s = (double)(float)ps_s; }   // float32 ps_pgw
     a.PS_out[c] = (float)ps_n;
     a.dps_out[c] = (float)dps_n;
     for (int l = 0; l < a.nlev; ++l) {
@@ -504,6 +584,26 @@ pgw_rewrite_kernel(const __grid_constant__ pgw_timestep_args a, const pgw_timest
         const float e = __fdividef(q * p_s, 0.622f + 0.378f * q);
         a.QV_out[off] = __fdividef(0.622f * e, p_n - 0.378f * e);
     }
+}
+
+// Latitude-band mode: the status block as float64 words that an element-wise MAX over the bands merges
+// (max error per iteration as is; minima negated; one word per error bit), and back.
+__global__ void pgw_band_pack_kernel(const pgw_timestep_status *s, double *w) {
+    const int i = threadIdx.x;
+    if (i < PGW_MAX_ITER) w[i] = __longlong_as_double((long long)s->maxerr[i]);
+    else if (i < PGW_MAX_ITER + 2) w[i] = -(double)s->stats[i - PGW_MAX_ITER];
+    else if (i < PGW_MAX_ITER + 34) w[i] = (double)((s->err >> (i - PGW_MAX_ITER - 2)) & 1u);
+    else if (i < PGW_BAND_WORDS) w[i] = -(double)s->first_k[i - PGW_MAX_ITER - 34];
+}
+__global__ void pgw_band_unpack_kernel(const double *w, pgw_timestep_status *s) {
+    const int i = threadIdx.x;
+    if (i < PGW_MAX_ITER) s->maxerr[i] = (uint64_t)__double_as_longlong(w[i]);
+    else if (i < PGW_MAX_ITER + 2) s->stats[i - PGW_MAX_ITER] = (float)(-w[i]);
+    else if (i == PGW_MAX_ITER + 2) {
+        uint32_t e = 0;
+        for (int b = 0; b < 32; ++b) if (w[PGW_MAX_ITER + 2 + b] != 0.0) e |= 1u << b;
+        s->err = e;
+    } else if (i >= PGW_MAX_ITER + 34 && i < PGW_BAND_WORDS) s->first_k[i - PGW_MAX_ITER - 34] = (int32_t)(-w[i]);
 }
 
 }  // namespace pgw
@@ -527,11 +627,12 @@ int stash_top(const double *ak, const double *bk, int nlev, double p_ref, double
     return lst;
 }
 
-size_t column_smem(int nlev, int nplev, int np, int nt) {
+size_t column_smem(int nlev, int nplev, int np, int nt, bool ref) {
     return sizeof(double) * 2 * (size_t)(nlev + 1) +                       // (ak, bk)
            (size_t)np * nt * (2 * sizeof(float)) +                         // (T_pgw, e_pgw) stash
            sizeof(float) * (size_t)(pgw::kRing + 1) * 4 * nt +             // cp.async ring
-           sizeof(float) * 2 * (size_t)nlev + sizeof(float) * 3 * (size_t)nplev + 16;
+           sizeof(float) * 2 * (size_t)nlev + sizeof(float) * 3 * (size_t)nplev + 16 +
+           (ref ? (size_t)np * nt * sizeof(float) : 0);                    // residual of the fp32 T_pgw
 }
 
 int validate(const pgw_timestep_args *a) {
@@ -564,11 +665,12 @@ pgw_column_plan plan_column(const pgw_timestep_args *a) {
     pgw_column_plan p;
     p.lst = stash_top(a->ak_host, a->bk_host, a->nlev, a->p_ref, a->ps_bound);
     p.np = a->nlev - p.lst;
-    p.smem = column_smem(a->nlev, a->nplev, p.np, kColumnThreads);
+    p.ref = (a->flags & PGW_FLAG_REF_DTYPES) != 0;
+    p.smem = column_smem(a->nlev, a->nplev, p.np, kColumnThreads, p.ref);
     p.tma = false;
     int lst_tma = 0;
     size_t smem_tma = 0;
-    if (tma_allowed() && !(a->flags & PGW_FLAG_DIRECT) && pgw_tma_eligible(a, p.lst, &lst_tma, &smem_tma)) {
+    if (tma_allowed() && !(a->flags & (PGW_FLAG_DIRECT | PGW_FLAG_REF_DTYPES)) && pgw_tma_eligible(a, p.lst, &lst_tma, &smem_tma)) {
         p.tma = true;
         p.lst = lst_tma;
         p.np = a->nlev - lst_tma;
@@ -606,27 +708,14 @@ int pgw_timestep(const pgw_timestep_args *a, void *stream) {
     if (rc != PGW_OK) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const pgw_column_plan plan = plan_column(a);
-    pgw::pgw_timestep_init_kernel<<<1, 64, 0, st>>>(a->maxerr, a->stats);
+    pgw::pgw_timestep_init_kernel<<<1, 64, 0, st>>>(a->maxerr, a->stats, a->err, a->first_k, a->poly_fallback);
     if (plan.tma) return pgw_launch_column_tma(a, plan, st);
 
-    auto kern = plan.fast ? pgw::pgw_column_kernel<kColumnThreads, true> : pgw::pgw_column_kernel<kColumnThreads, false>;
-    static thread_local size_t configured[2] = {0, 0};
-    size_t &conf = configured[plan.fast ? 1 : 0];
-    if (plan.smem > conf) {
-        int dev = 0, max_optin = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-        if (plan.smem > (size_t)max_optin) {
-            pgw_set_error("column stash needs %zu B of shared memory (%d levels below p_ref), device allows %d",
-                          plan.smem, plan.np, max_optin);
-            return PGW_E_SMEM;
-        }
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem) != cudaSuccess)
-            return pgw_check_launch("cudaFuncSetAttribute");
-        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
-                             cudaSharedmemCarveoutMaxShared);
-        conf = plan.smem;
-    }
+    const int variant = plan.ref ? 2 : (plan.fast ? 1 : 0);
+    auto kern = plan.ref ? pgw::pgw_column_kernel<kColumnThreads, false, true>
+                         : (plan.fast ? pgw::pgw_column_kernel<kColumnThreads, true, false>
+                                      : pgw::pgw_column_kernel<kColumnThreads, false, false>);
+    if ((rc = pgw_ensure_smem((const void *)kern, variant, plan.smem, plan.np)) != PGW_OK) return rc;
     const unsigned grid = (unsigned)((a->ncol + kColumnThreads - 1) / kColumnThreads);
     kern<<<grid, kColumnThreads, plan.smem, st>>>(*a, plan.lst, plan.np);
     return pgw_check_launch("pgw_column_kernel");
@@ -640,6 +729,45 @@ int pgw_timestep_finalize(const pgw_timestep_args *a, pgw_timestep_result *resul
     const unsigned grid = (unsigned)((a->ncol + 255) / 256);
     pgw::pgw_rewrite_kernel<<<grid, 256, 0, st>>>(*a, result_dev);
     return pgw_check_launch("pgw_timestep_finalize");
+}
+
+long long pgw_sizeof_timestep_status(void) { return (long long)sizeof(pgw_timestep_status); }
+
+static bool status_matches(const pgw_timestep_args *a, pgw_timestep_status *s) {
+    return s && a->maxerr == s->maxerr && a->stats == s->stats && a->err == &s->err && a->first_k == s->first_k &&
+           a->poly_fallback == &s->poly_fallback;
+}
+
+int pgw_timestep_finish(const pgw_timestep_args *a, pgw_timestep_status *status_dev,
+                        pgw_timestep_status *status_host, void *stream) {
+    if (!a || !status_matches(a, status_dev)) return PGW_E_INVALID;
+    int rc = pgw_timestep_finalize(a, &status_dev->result, stream);
+    if (rc != PGW_OK) return rc;
+    if (status_host &&
+        cudaMemcpyAsync(status_host, status_dev, sizeof(pgw_timestep_status), cudaMemcpyDeviceToHost,
+                        (cudaStream_t)stream) != cudaSuccess)
+        return pgw_check_launch("cudaMemcpyAsync(status)");
+    return PGW_OK;
+}
+
+int pgw_timestep_run(const pgw_timestep_args *a, pgw_timestep_status *status_dev,
+                     pgw_timestep_status *status_host, int run_flags, void *stream) {
+    if (!a || !status_matches(a, status_dev)) return PGW_E_INVALID;
+    int rc = pgw_timestep(a, stream);
+    if (rc != PGW_OK || (run_flags & PGW_RUN_NO_FINALIZE)) return rc;
+    return pgw_timestep_finish(a, status_dev, status_host, stream);
+}
+
+int pgw_band_pack(const pgw_timestep_status *status_dev, double *words_dev, void *stream) {
+    if (!status_dev || !words_dev) return PGW_E_INVALID;
+    pgw::pgw_band_pack_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(status_dev, words_dev);
+    return pgw_check_launch("pgw_band_pack");
+}
+
+int pgw_band_unpack(const double *words_dev, pgw_timestep_status *status_dev, void *stream) {
+    if (!status_dev || !words_dev) return PGW_E_INVALID;
+    pgw::pgw_band_unpack_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(words_dev, status_dev);
+    return pgw_check_launch("pgw_band_unpack");
 }
 
 }  // extern "C"

@@ -28,7 +28,7 @@ VARS_3D = ("ta", "hur", "ua", "va", "zg")
 VARS_PACKED = ("ta", "hur", "ua", "va")       # one float4 per pressure node and column on the device
 VARS_2D = ("tas", "hurs", "ps_hist", "ts", "tos", "siconc")
 
-_STATUS_BYTES = 8 * N.PGW_MAX_ITER + 16 + 8 + 8     # maxerr | result | stats | err,pad
+_STATUS_BYTES = C.sizeof(N.TimestepStatus)
 
 MSG_TOP = ("ERA5 top pressure is lower than climate delta top pressure. If you are certain that "
            "you do not need the data beyond to upper-most pressure level of the climate delta, "
@@ -65,6 +65,7 @@ class DeltaSet:
     def __init__(self, deltas, device="cuda"):
         self.device = torch.device(device)
         self.vars = {}
+        staged = {}
         for name in VARS_3D + VARS_2D:
             if name not in deltas:
                 raise KeyError("climate delta %r missing" % name)
@@ -76,10 +77,10 @@ class DeltaSet:
                 data = torch.as_tensor(np.asarray(data))
             if len(keep) != len(stamps):
                 data = data[torch.as_tensor(keep, device=data.device)]
-            data = data.to(self.device, torch.float32).contiguous()
             plev = None if d.get("plev") is None else np.asarray(d["plev"], dtype=np.float64)
-            self.vars[name] = dict(time=stamps[keep], plev=plev, data=data)
-        self.shape2d = tuple(self.vars["ts"]["data"].shape[-2:])
+            self.vars[name] = dict(time=stamps[keep], plev=plev, data=None)
+            staged[name] = data
+        self.shape2d = tuple(staged["ts"].shape[-2:])
         self.ncol = self.shape2d[0] * self.shape2d[1]
         plev = self.vars["ta"]["plev"]
         for name in ("hur", "ua", "va"):
@@ -96,9 +97,26 @@ class DeltaSet:
         for name in ("hur", "ua", "va"):
             if not np.array_equal(self.vars[name]["time"], stamps):
                 raise ValueError("ta, hur, ua, va deltas must share their time stamps")
-        self.d4 = torch.stack([self.vars[n]["data"] for n in VARS_PACKED], dim=-1).contiguous()
+            if tuple(staged[name].shape) != tuple(staged["ta"].shape):
+                raise ValueError("ta, hur, ua, va deltas must share their shape")
+        # ONE arena holds the whole climatology (the packed float4 nodes first: 16-byte aligned), so that
+        # replicating it to the other GPUs is one NCCL broadcast (parallel.broadcast_deltas)
+        shapes = [("d4", tuple(staged["ta"].shape) + (4,))] + \
+                 [(n, tuple(staged[n].shape)) for n in ("zg",) + VARS_2D]
+        offs, total = {}, 0
+        for name, shp in shapes:
+            offs[name] = total
+            total += (int(np.prod(shp)) + 3) // 4 * 4
+        self.arena = torch.empty(total, device=self.device, dtype=torch.float32)
+        view = lambda name, shp: self.arena[offs[name]:offs[name] + int(np.prod(shp))].view(shp)
+        self.d4 = view(*shapes[0])
         for i, name in enumerate(VARS_PACKED):
+            self.d4[..., i].copy_(staged.pop(name).to(self.device, torch.float32))
             self.vars[name]["data"] = self.d4[..., i]
+        for name, shp in shapes[1:]:
+            v = view(name, shp)
+            v.copy_(staged.pop(name).to(self.device, torch.float32))
+            self.vars[name]["data"] = v
         self._brackets = {}
         self.ts_clim = None
         self.refresh_derived()
@@ -109,10 +127,12 @@ class DeltaSet:
         self.ts_clim = torch.empty(ts.shape[1:], device=self.device, dtype=torch.float32)
         N.check(N.lib.pgw_time_mean_f32(_ptr(ts), ts.shape[0], _ptr(self.ts_clim), self.ncol, _stream()),
                 "pgw_time_mean_f32")
+        # the pipelines run on their own streams, which do not wait for the stream the arena was filled on
+        torch.cuda.current_stream().synchronize()
 
     def tensors(self):
-        """All device tensors in a fixed order (for the NCCL broadcast)."""
-        return [self.d4] + [self.vars[n]["data"] for n in ("zg",) + VARS_2D]
+        """The device memory that holds the climatology (for the NCCL broadcast): one arena."""
+        return [self.arena]
 
     def bracket(self, name, when):
         key = (name, when)
@@ -142,10 +162,21 @@ class DeltaSet:
 class Pending:
     """A submitted timestep; ``result()`` waits for it and applies the host-side checks."""
 
-    def __init__(self, engine, args, out, status_host, event, ctx):
+    def __init__(self, engine, args, out, ws, ctx):
         self.engine, self.args, self.out = engine, args, out
-        self.status_host, self.event, self.ctx = status_host, event, ctx
+        self.ws, self.ctx = ws, ctx
+        self.status = None              # private copy of the status block once the timestep has finished
         self._done = None
+
+    def snapshot(self):
+        """Wait for the timestep and take its status block out of the slot's pinned buffer (which the
+        next submit on the same slot overwrites)."""
+        if self.status is None:
+            self.ws["event"].synchronize()
+            self.status = N.TimestepStatus.from_buffer_copy(self.ws["status_host"].numpy())
+            if self.ws.get("inflight") is self:
+                self.ws["inflight"] = None
+        return self.status
 
     def result(self):
         if self._done is None:
@@ -191,8 +222,8 @@ class PGWEngine:
 
     # ------------------------------------------------------------------ workspace
     def _workspace(self, ncol, max_iter, slot=0):
-        """Per-slot scratch (iteration trajectory + status words).  Timesteps in flight on
-        different streams must use different slots."""
+        """Per-slot scratch: iteration trajectory, the status block on the device and its pinned host
+        copy, one event.  Timesteps in flight on different streams must use different slots."""
         key = (ncol, max_iter, slot)
         ws = self._ws.get(key)
         if ws is None:
@@ -200,7 +231,11 @@ class PGWEngine:
             ws = dict(
                 traj=torch.empty((max_iter, ncol), device=self.device, dtype=torch.float32),
                 status=torch.zeros(_STATUS_BYTES, device=self.device, dtype=torch.uint8),
+                status_host=torch.zeros(_STATUS_BYTES, dtype=torch.uint8, pin_memory=True),
+                event=torch.cuda.Event(), inflight=None,
             )
+            if self.group is not None:
+                ws["band_words"] = torch.zeros(N.BAND_WORDS, device=self.device, dtype=torch.float64)
             self._ws[key] = ws
         return ws
 
@@ -225,32 +260,38 @@ class PGWEngine:
         a, f, out, ws, k_spec, k_max = self._fill_args(era, era_step_dt, out, k_spec, slot)
         if direct:
             a.flags |= N.FLAG_DIRECT          # every parked level integrated in every iteration
-        status = ws["status"]
-        base = status.data_ptr()
-        result_ptr = base + 8 * N.PGW_MAX_ITER
-        status[8 * N.PGW_MAX_ITER + 24:].zero_()                          # clear the sticky error word
+        if ws["inflight"] is not None:        # the slot's pinned status block is about to be reused
+            ws["inflight"].snapshot()
         st = _stream()
+        sdev, shost = C.c_void_p(ws["status"].data_ptr()), C.c_void_p(ws["status_host"].data_ptr())
         if self.kernel_events is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        N.check(N.lib.pgw_timestep(C.byref(a), st), "pgw_timestep")
-        if self.kernel_events is not None:
-            e1.record()
-            self.kernel_events.append((e0, e1))
+        if self.group is None and self.kernel_events is None:
+            # init, column kernel, convergence scan, rewrite and the status copy in one call
+            N.check(N.lib.pgw_timestep_run(C.byref(a), sdev, shost, 0, st), "pgw_timestep_run")
+        else:
+            N.check(N.lib.pgw_timestep_run(C.byref(a), sdev, None, N.RUN_NO_FINALIZE, st), "pgw_timestep_run")
+            if self.kernel_events is not None:
+                e1.record()
+                self.kernel_events.append((e0, e1))
+            if self.group is not None:
+                # latitude-band mode: the stopping rule is global over all bands (step_03:189,308).  ONE
+                # collective merges the whole status block: max error per iteration, error bits, minima.
+                import torch.distributed as dist
+                w = ws["band_words"]
+                N.check(N.lib.pgw_band_pack(sdev, C.c_void_p(w.data_ptr()), st), "pgw_band_pack")
+                dist.all_reduce(w, op=dist.ReduceOp.MAX, group=self.group)
+                N.check(N.lib.pgw_band_unpack(C.c_void_p(w.data_ptr()), sdev, st), "pgw_band_unpack")
+                self.stats["launches"] += 2
+            N.check(N.lib.pgw_timestep_finish(C.byref(a), sdev, shost, st), "pgw_timestep_finish")
         self.stats["launches"] += 4
-        if self.group is not None:
-            # latitude-band mode: the stopping rule is global over all bands
-            import torch.distributed as dist
-            maxerr = status[:8 * N.PGW_MAX_ITER].view(torch.float64)
-            dist.all_reduce(maxerr, op=dist.ReduceOp.MAX, group=self.group)
-        N.check(N.lib.pgw_timestep_finalize(C.byref(a), C.c_void_p(result_ptr), st), "pgw_timestep_finalize")
-        host = torch.empty(_STATUS_BYTES, dtype=torch.uint8, pin_memory=True)
-        host.copy_(status, non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record()
+        ws["event"].record()
         ctx = dict(era=era, when=era_step_dt, ignore_top=ignore_top_pressure_error, k_spec=k_spec,
                    k_max=k_max, keep=(f, a), file_name=file_name, slot=slot, direct=direct)
-        return Pending(self, a, out, host, ev, ctx)
+        p = Pending(self, a, out, ws, ctx)
+        ws["inflight"] = p
+        return p
 
     def _fill_args(self, era, era_step_dt, out=None, k_spec=None, slot=0):
         """Validate the ERA5 fields and fill a ``pgw_timestep_args`` for them.  Returns
@@ -324,23 +365,31 @@ class PGWEngine:
         a.dps_out = out["delta_ps"].data_ptr()
         a.dps_traj = ws["traj"].data_ptr()
         base = status.data_ptr()
-        a.maxerr = base
-        a.stats = base + 8 * N.PGW_MAX_ITER + 16
-        a.err = base + 8 * N.PGW_MAX_ITER + 24
+        S = N.TimestepStatus
+        a.maxerr = base + S.maxerr.offset
+        a.stats = base + S.stats.offset
+        a.err = base + S.err.offset
+        a.first_k = base + S.first_k.offset
+        a.poly_fallback = base + S.poly_fallback.offset
+        if getattr(settings, "i_reference_dtypes", 0):
+            a.flags |= N.FLAG_REF_DTYPES
         return a, f, out, ws, k_spec, k_max
 
     # ------------------------------------------------------------------ completion
     def _complete(self, p):
-        p.event.synchronize()
-        raw = p.status_host.numpy()
-        nmi = N.PGW_MAX_ITER
-        maxerr = raw[:8 * nmi].view(np.float64)
-        n_iter, converged, rewritten, _ = raw[8 * nmi:8 * nmi + 16].view(np.int32)
-        min_targ_p, min_src_p = raw[8 * nmi + 16:8 * nmi + 24].view(np.float32)
-        err = int(raw[8 * nmi + 24:8 * nmi + 28].view(np.uint32)[0])
+        st = p.snapshot()
+        maxerr = np.frombuffer(st.maxerr, dtype=np.float64)
+        n_iter, converged, rewritten = st.result.n_iter, st.result.converged, st.result.rewritten
+        min_targ_p, min_src_p = float(st.stats[0]), float(st.stats[1])
+        err = int(st.err)
         ctx = p.ctx
-        if self.group is not None:
-            err, min_targ_p, min_src_p = self._merge_status(err, min_targ_p, min_src_p)
+        # The kernel runs k_spec iterations for every column; the reference stops after N.  A ps-dependent
+        # condition that only fired in an iteration the reference never ran did not happen there.
+        n_ran = int(n_iter) if converged else ctx["k_spec"]
+        if (err & N.ERR_PREF_BELOW_SFC) and st.first_k[0] >= n_ran:
+            err &= ~N.ERR_PREF_BELOW_SFC
+        if (err & N.ERR_PS_BOUND) and st.first_k[1] >= n_ran:
+            err &= ~N.ERR_PS_BOUND
         if err & N.ERR_PS_HIST_RANGE:
             raise ValueError()                                           # functions.py:360-361
         if (min_targ_p < min_src_p or min_targ_p < float(np.min(self.deltas.plev))) \
@@ -370,20 +419,11 @@ class PGWEngine:
         res = dict(p.out)
         res["n_iter"] = int(n_iter)
         res["phi_max_errors"] = [float(x) for x in maxerr[:int(n_iter)]]
+        res["poly_fallback"] = int(st.poly_fallback)
         if settings.i_debug >= 2:
             for it, e in enumerate(res["phi_max_errors"], 1):
                 print("### iteration {:03d}, phi max error: {}".format(it, e))
         return res
-
-    def _merge_status(self, err, min_targ_p, min_src_p):
-        import torch.distributed as dist
-        bits = torch.tensor([(err >> i) & 1 for i in range(32)], device=self.device, dtype=torch.int32)
-        dist.all_reduce(bits, op=dist.ReduceOp.MAX, group=self.group)
-        mins = torch.tensor([min_targ_p, min_src_p], device=self.device, dtype=torch.float32)
-        dist.all_reduce(mins, op=dist.ReduceOp.MIN, group=self.group)
-        err = int(sum(int(b) << i for i, b in enumerate(bits.tolist())))
-        m = mins.tolist()
-        return err, m[0], m[1]
 
     def apply(self, era, era_step_dt, **kw):
         """Synchronous form of ``submit``: returns the output dict (device tensors).  The settings

@@ -45,19 +45,28 @@ def decide_n_iter(maxerr, thresh):
     return 0
 
 
-def broadcast_deltas(deltas, src=0, group=None):
-    """NCCL-broadcast every tensor of a ``DeltaSet`` from ``src``; returns elapsed ms."""
+def broadcast_deltas(deltas, src=0, group=None, info=None):
+    """NCCL-broadcast the climatology of a ``DeltaSet`` from ``src`` -- ONE collective over its arena, after a
+    one-element collective that makes NCCL set up its communicator and channels outside the timing.  Returns
+    the elapsed ms of the broadcast itself; ``info`` (a dict) also receives bytes and GB/s."""
     import torch
     import torch.distributed as dist
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    warm = torch.zeros(1, device=deltas.device)
+    dist.broadcast(warm, src=src, group=group)
     torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    nbytes = 0
     for t in deltas.tensors():
         dist.broadcast(t, src=src, group=group)
+        nbytes += t.numel() * t.element_size()
     e1.record()
     torch.cuda.synchronize()
     deltas.refresh_derived()
-    return e0.elapsed_time(e1)
+    ms = e0.elapsed_time(e1)
+    if info is not None:
+        info.update(bytes=nbytes, ms=ms, gb_per_s=nbytes / ms / 1e6 if ms > 0 else None, collectives=len(deltas.tensors()))
+    return ms
 
 
 def _parse_cpulist(text):
@@ -94,16 +103,26 @@ def bind_to_gpu_numa(device_index):
         return None
 
 
-def _worker(payload):
-    func, kwargs, worker_slot = payload
+def _init_worker(counter):
+    """Pool initializer: every worker process takes ONE GPU (worker index % device_count) for its whole
+    lifetime -- whichever tasks the pool hands it later -- and binds to that GPU's NUMA node."""
+    with counter.get_lock():
+        idx = counter.value
+        counter.value += 1
+    if os.environ.get("PGW_ITERMP_NO_GPU"):       # CPU-only tasks (bench.py's reference arm)
+        return
     try:
         import torch
         if torch.cuda.is_available():
-            dev = worker_slot % torch.cuda.device_count()
+            dev = idx % torch.cuda.device_count()
             torch.cuda.set_device(dev)
             bind_to_gpu_numa(dev)
     except ImportError:
         pass
+
+
+def _worker(payload):
+    func, kwargs = payload
     return func(**kwargs)
 
 
@@ -111,10 +130,14 @@ class IterMP:
     """Same interface as the reference's ``IterMP`` (parallel.py:36-68):
     ``IterMP(njobs, run_async).run(func, fargs, step_args)`` then ``.output``."""
 
-    def __init__(self, njobs=None, run_async=False):
+    def __init__(self, njobs=None, run_async=False, start_method="spawn", quiet=False):
+        """``start_method``/``quiet`` are not in the reference: workers that use a GPU must be spawned (a forked
+        child cannot use CUDA); CPU-only tasks may fork."""
         self.run_async = run_async
         self.njobs = 1 if njobs is None else int(njobs)
-        print('IterMP: njobs = ' + str(self.njobs))
+        self.start_method = start_method
+        if not quiet:
+            print('IterMP: njobs = ' + str(self.njobs))
         self.output = None
 
     def run(self, func, fargs={}, step_args=None):
@@ -124,9 +147,9 @@ class IterMP:
             kw.update(step_args[i])
             tasks.append(kw)
         if self.njobs > 1:
-            ctx = mp.get_context("spawn")
-            with ctx.Pool(processes=self.njobs) as pool:
-                payload = [(func, kw, i % self.njobs) for i, kw in enumerate(tasks)]
+            ctx = mp.get_context(self.start_method)
+            with ctx.Pool(processes=self.njobs, initializer=_init_worker, initargs=(ctx.Value("i", 0),)) as pool:
+                payload = [(func, kw) for kw in tasks]
                 if self.run_async:
                     self.output = pool.map_async(_worker, payload).get()
                 else:

@@ -65,6 +65,15 @@ thresh_phi_ref_max_error = 0.15
 max_n_iter = 20
 i_reinterp = 0
 
+# Not in the reference's settings.py.  The reference never casts, so what it computes in follows from the
+# dtypes of the ERA5 file: with float32 PS and FIS (every real file) delta_ps / ps_pgw are float32 and the
+# half-level geopotential is a float32 running sum (step_03_apply_to_era.py:186-195, functions.py:141),
+# which adds ~1e-2 m2/s2 of rounding noise to the geopotential error and ~3e-2 Pa to ps_pgw.
+#   0 (default): float64 accumulation = the reference on a file that stores PS and FIS as double;
+#                thresholds below ~1e-2 m2/s2 converge (the reference's float32 path cannot reach them).
+#   1: reproduce the float32 rounding steps of the reference exactly where it applies them.
+i_reference_dtypes = 0
+
 
 def _load_user_settings():
     path = _os.environ.get('PGW_SETTINGS')
