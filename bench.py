@@ -344,13 +344,22 @@ def run_ours(a):
     base = datetime(2006, 8, 1, 0)
     when = lambda i: base + timedelta(hours=6 * ((i * world + rank) % 124))
 
+    streams = [torch.cuda.Stream(device=dev) for _ in range(a.streams)] if a.streams > 1 else None
+
     def run_steps(n, collect=None):
         """n timesteps, up to `nslot` in flight: the host checks the status of a timestep (iteration count,
-        error bits; may trigger a rerun) while the next ones are already queued behind it."""
+        error bits; may trigger a rerun) while the next ones are already queued behind it.  With --streams S > 1
+        consecutive timesteps alternate between S streams (slot i always on the same stream), so the last,
+        partly filled wave of one timestep's column kernel overlaps the first wave of the next."""
         pend = []
         for i in range(n):
-            pend.append(eng.submit(ring[i % a.ring], when(i), out=outs[i % nslot], ignore_top_pressure_error=True,
-                                   slot=i % nslot))
+            if streams:
+                with torch.cuda.stream(streams[(i % nslot) % a.streams]):
+                    pend.append(eng.submit(ring[i % a.ring], when(i), out=outs[i % nslot],
+                                           ignore_top_pressure_error=True, slot=i % nslot))
+            else:
+                pend.append(eng.submit(ring[i % a.ring], when(i), out=outs[i % nslot], ignore_top_pressure_error=True,
+                                       slot=i % nslot))
             if len(pend) >= nslot:
                 r = pend.pop(0).result()
                 if collect is not None:
@@ -374,9 +383,14 @@ def run_ours(a):
     if sampler:
         sampler.mark_start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_host0 = time.perf_counter()
     ev0.record()
+    if streams:
+        for st in streams:
+            st.wait_event(ev0)
     last = run_steps(a.steps, n_iters)
+    if streams:
+        for st in streams:
+            torch.cuda.current_stream().wait_stream(st)
     ev1.record()
     import ctypes
     from pgw4era5_b200 import _native
@@ -501,7 +515,7 @@ def run_ours(a):
                        "grid": a.grid, "ring": a.ring,
                        "l2": "inputs cycle through %d distinct 2.3 GB timesteps (>> 126 MB L2)" % a.ring,
                        "parallelism": "timestep-sharded x%d" % world, "numa_node": numa,
-                       "timesteps_in_flight": nslot,
+                       "timesteps_in_flight": nslot, "streams": a.streams,
                        "n_iter": {"min": int(min(n_iters)), "max": int(max(n_iters)), "steps": len(n_iters)},
                        "engine": dict(eng.stats),
                        "host_us_per_submit": host_us_submit, "host_us_fill_args": host_us_fill,
@@ -527,6 +541,7 @@ def main():
     ap.add_argument("--e2e-slots", type=int, default=2, help="timesteps in flight in the host-buffer pipeline")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--inflight", type=int, default=4, help="timesteps queued before the host checks the oldest")
+    ap.add_argument("--streams", type=int, default=1, help="CUDA streams the timesteps alternate between")
     ap.add_argument("--no-latband", action="store_true")
     ap.add_argument("--latband-snapshots", type=int, default=100)
     a = ap.parse_args()

@@ -143,6 +143,54 @@ __device__ __forceinline__ float thermo_e_pgw(bool cold, float p, float t, float
     const float rh_pgw = fmaf(100.0f * q * p, fast_rcp((0.622f + 0.378f * q) * es_e), dhur);
     return rh_pgw * 0.01f * es_p;
 }
+// The same for TWO levels at once with the packed float32 pair instructions of sm_100 (FADD2 / FMUL2 / FFMA2):
+// the sweep handles level pairs, whose thermodynamics are two independent, identical instruction sequences; packed,
+// every add/multiply of the pair is one issue slot instead of two (MUFU and the selects stay scalar).  Same
+// operations in the same order per lane as thermo_e_pgw.
+__device__ __forceinline__ float2 thermo_e_pgw_x2(bool cold, float2 p, float2 t, float2 q, float2 dta, float2 dhur) {
+    const auto S = [](float a) { return make_float2(a, a); };
+    const float2 tm273 = __fadd2_rn(t, S(-273.0f));
+    const float2 dTe = __fadd2_rn(tm273, S(-0.16f)), tkp = __fadd2_rn(tm273, dta);
+    const float2 dTp = __fadd2_rn(tm273, __fadd2_rn(dta, S(-0.16f)));
+    constexpr float kCw = 17.502f * 1.4426950408889634f, kCi = 22.587f * 1.4426950408889634f;
+    float2 es_e, es_p;
+    if (cold) {
+        const float2 de = __fadd2_rn(tm273, S(273.0f + 0.7f)), dp = __fadd2_rn(tkp, S(273.0f + 0.7f));
+        const float2 dd = __fmul2_rn(de, dp);
+        const float2 rr = make_float2(fast_rcp(dd.x), fast_rcp(dd.y));
+        const float2 ae = __fmul2_rn(__fmul2_rn(S(kCi), dTe), __fmul2_rn(rr, dp));
+        const float2 ap = __fmul2_rn(__fmul2_rn(S(kCi), dTp), __fmul2_rn(rr, de));
+        es_e = __fmul2_rn(S(611.21f), make_float2(fast_ex2(ae.x), fast_ex2(ae.y)));
+        es_p = __fmul2_rn(S(611.21f), make_float2(fast_ex2(ap.x), fast_ex2(ap.y)));
+    } else {
+        const float2 dew = __fadd2_rn(tm273, S(273.0f - 32.19f)), dei = __fadd2_rn(tm273, S(273.0f + 0.7f));
+        const float2 dpw = __fadd2_rn(tkp, S(273.0f - 32.19f)), dpi = __fadd2_rn(tkp, S(273.0f + 0.7f));
+        const float2 pe = __fmul2_rn(dew, dei), pp = __fmul2_rn(dpw, dpi);
+        const float2 pq = __fmul2_rn(pe, pp);
+        const float2 rr = make_float2(fast_rcp(pq.x), fast_rcp(pq.y));
+        const float2 re = __fmul2_rn(rr, pp), rp = __fmul2_rn(rr, pe);
+        const float2 cwe = __fmul2_rn(S(kCw), dTe), cie = __fmul2_rn(S(kCi), dTe);
+        const float2 cwp = __fmul2_rn(S(kCw), dTp), cip = __fmul2_rn(S(kCi), dTp);
+        const float2 a1 = __fmul2_rn(cwe, __fmul2_rn(re, dei)), a2 = __fmul2_rn(cie, __fmul2_rn(re, dew));
+        const float2 a3 = __fmul2_rn(cwp, __fmul2_rn(rp, dpi)), a4 = __fmul2_rn(cip, __fmul2_rn(rp, dpw));
+        const float2 ew_e = make_float2(fast_ex2(a1.x), fast_ex2(a1.y)), ei_e = make_float2(fast_ex2(a2.x), fast_ex2(a2.y));
+        const float2 ew_p = make_float2(fast_ex2(a3.x), fast_ex2(a3.y)), ei_p = make_float2(fast_ex2(a4.x), fast_ex2(a4.y));
+        const float2 r_e = __fmul2_rn(__fadd2_rn(dTe, S(23.0f)), S(1.0f / 23.0f));
+        const float2 r_p = __fmul2_rn(__fadd2_rn(dTp, S(23.0f)), S(1.0f / 23.0f));
+        const float2 q_e = __fmul2_rn(r_e, r_e), q_p = __fmul2_rn(r_p, r_p);
+        const auto sel = [](float dT, float sq) { return dT >= 0.0f ? 1.0f : (dT <= -23.0f ? 0.0f : sq); };   // NaN stays NaN
+        const float2 al_e = make_float2(sel(dTe.x, q_e.x), sel(dTe.y, q_e.y));
+        const float2 al_p = make_float2(sel(dTp.x, q_p.x), sel(dTp.y, q_p.y));
+        const float2 one = S(1.0f);
+        const float2 be = __fadd2_rn(one, make_float2(-al_e.x, -al_e.y)), bp = __fadd2_rn(one, make_float2(-al_p.x, -al_p.y));
+        es_e = __fmul2_rn(S(611.21f), __ffma2_rn(al_e, ew_e, __fmul2_rn(be, ei_e)));
+        es_p = __fmul2_rn(S(611.21f), __ffma2_rn(al_p, ew_p, __fmul2_rn(bp, ei_p)));
+    }
+    const float2 den = __fmul2_rn(__ffma2_rn(S(0.378f), q, S(0.622f)), es_e);
+    const float2 rd = make_float2(fast_rcp(den.x), fast_rcp(den.y));
+    const float2 rh = __ffma2_rn(__fmul2_rn(__fmul2_rn(S(100.0f), q), p), rd, dhur);
+    return __fmul2_rn(__fmul2_rn(rh, S(0.01f)), es_p);
+}
 __device__ __forceinline__ bool is_cold(float t, float dta) { return fmaxf(t, t + dta) <= 250.0f; }   // conservative
 
 // specific humidity from vapour pressure (functions.py:66-72), p = akm + ps * bkm

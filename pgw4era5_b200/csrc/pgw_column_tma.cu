@@ -327,10 +327,20 @@ pgw_column_tma_kernel(const __grid_constant__ pgw_timestep_args a, const __grid_
         // t == 0: exact node hit or constant extrapolation -> the node value itself (NaN-safe)
         const bool ex = (t == 0.0f);
         Dlt d;
+#ifdef PGW_X2
+        const float2 tt = make_float2(t, t);
+        const float2 ab = __ffma2_rn(tt, make_float2(x_d.x, x_d.y), make_float2(x_lo.x, x_lo.y));
+        const float2 cd = __ffma2_rn(tt, make_float2(x_d.z, x_d.w), make_float2(x_lo.z, x_lo.w));
+        d.ta = ex ? x_lo.x : ab.x;
+        d.hur = ex ? x_lo.y : ab.y;
+        d.ua = ex ? x_lo.z : cd.x;
+        d.va = ex ? x_lo.w : cd.y;
+#else
         d.ta = ex ? x_lo.x : fmaf(t, x_d.x, x_lo.x);
         d.hur = ex ? x_lo.y : fmaf(t, x_d.y, x_lo.y);
         d.ua = ex ? x_lo.z : fmaf(t, x_d.z, x_lo.z);
         d.va = ex ? x_lo.w : fmaf(t, x_d.w, x_lo.w);
+#endif
         return d;
     };
     auto walk = [&](float p) { step_to(p); return interp(p); };
@@ -534,7 +544,12 @@ pgw_column_tma_kernel(const __grid_constant__ pgw_timestep_args a, const __grid_
         float *const sl = ring + (j % kTmaSlots) * 8 * NT + tid;
         // the walks need no slot data: they cover the round trip of the barrier probe (~100 cycles)
         const bool ready = mbar_test(bar_full + (j % kTmaSlots), (j / kTmaSlots) & 1);
+#ifdef PGW_X2
+        const float2 p01 = __ffma2_rn(make_float2(ps_f, ps_f), make_float2(mm0.y, mm1.y), make_float2(mm0.x, mm1.x));
+        const float p0 = p01.x, p1 = p01.y;
+#else
         const float p0 = fmaf(ps_f, mm0.y, mm0.x), p1 = fmaf(ps_f, mm1.y, mm1.x);
+#endif
         Dlt d0 = walk(p0);
         Dlt d1 = walk(p1);
         if (stale) refresh();
@@ -543,11 +558,26 @@ pgw_column_tma_kernel(const __grid_constant__ pgw_timestep_args a, const __grid_
         const float t1 = sl[0], q1 = sl[2 * NT], u1 = sl[4 * NT], v1 = sl[6 * NT];     // row 0: level l-1
         if (__any_sync(0xffffffffu, bot_on)) { sfc_override(p0, d0); sfc_override(p1, d1); }
         const bool cold = __all_sync(0xffffffffu, is_cold(t0, d0.ta) && is_cold(t1, d1.ta));
+#ifdef PGW_X2
+        const float2 e01 = thermo_e_pgw_x2(cold, make_float2(p0, p1), make_float2(t0, t1), make_float2(q0, q1),
+                                           make_float2(d0.ta, d1.ta), make_float2(d0.hur, d1.hur));
+        const float e0 = e01.x, e1 = e01.y;
+#else
         const float e0 = thermo_e_pgw(cold, p0, t0, q0, d0.ta, d0.hur);
         const float e1 = thermo_e_pgw(cold, p1, t1, q1, d1.ta, d1.hur);
+#endif
+#ifdef PGW_X2
+        const float2 tp01 = __fadd2_rn(make_float2(t0, t1), make_float2(d0.ta, d1.ta));
+        const float2 up01 = __fadd2_rn(make_float2(u0, u1), make_float2(d0.ua, d1.ua));
+        const float2 vp01 = __fadd2_rn(make_float2(v0, v1), make_float2(d0.va, d1.va));
+        const float tp0 = tp01.x, tp1 = tp01.y;
+        sl[NT] = tp0; sl[5 * NT] = up01.x; sl[7 * NT] = vp01.x;
+        sl[0] = tp1; sl[4 * NT] = up01.y; sl[6 * NT] = vp01.y;
+#else
         const float tp0 = t0 + d0.ta, tp1 = t1 + d1.ta;   // == (float)((double)t + (double)dta)
         sl[NT] = tp0; sl[5 * NT] = u0 + d0.ua; sl[7 * NT] = v0 + d0.va;
         sl[0] = tp1; sl[4 * NT] = u1 + d1.ua; sl[6 * NT] = v1 + d1.va;
+#endif
         if (parked) {
             fence_proxy_async();
             mbar_arrive(bar_done + (j % kTmaSlots));
@@ -558,8 +588,17 @@ pgw_column_tma_kernel(const __grid_constant__ pgw_timestep_args a, const __grid_
             era_layer(l, p0, mm0.y, t0, q0, d0.ta, tp0, e0);
             era_layer(l - 1, p1, mm1.y, t1, q1, d1.ta, tp1, e1);
         } else {
+#ifdef PGW_X2
+            const float2 pn = __ffma2_rn(make_float2(psn_f, psn_f), make_float2(mm0.y, mm1.y), make_float2(mm0.x, mm1.x));
+            const float2 den = __ffma2_rn(make_float2(-0.378f, -0.378f), e01, pn);
+            const float2 qv = __fmul2_rn(__fmul2_rn(make_float2(0.622f, 0.622f), e01),
+                                         make_float2(fast_rcp(den.x), fast_rcp(den.y)));
+            sl[3 * NT] = qv.x;                            // functions.py:66-72 with the adjusted ps
+            sl[2 * NT] = qv.y;
+#else
             sl[3 * NT] = qv_from_e(e0, psn_f, mm0);       // functions.py:66-72 with the adjusted ps
             sl[2 * NT] = qv_from_e(e1, psn_f, mm1);
+#endif
             fence_proxy_async();
             mbar_arrive(bar_done + (j % kTmaSlots));
         }

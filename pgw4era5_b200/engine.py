@@ -117,14 +117,15 @@ class DeltaSet:
             v = view(name, shp)
             v.copy_(staged.pop(name).to(self.device, torch.float32))
             self.vars[name]["data"] = v
-        self._brackets = {}
+        self._brackets, self._moved, self._time_group, self._time_ids, self._lay = {}, {}, {}, {}, {}
         self.ts_clim = None
         self.refresh_derived()
 
     def refresh_derived(self):
         """Annual mean of the ts delta (step_03_apply_to_era.py:134-136), computed once."""
         ts = self.vars["ts"]["data"]
-        self.ts_clim = torch.empty(ts.shape[1:], device=self.device, dtype=torch.float32)
+        if self.ts_clim is None or tuple(self.ts_clim.shape) != tuple(ts.shape[1:]):     # else in place: its address
+            self.ts_clim = torch.empty(ts.shape[1:], device=self.device, dtype=torch.float32)   # is cached in args
         N.check(N.lib.pgw_time_mean_f32(_ptr(ts), ts.shape[0], _ptr(self.ts_clim), self.ncol, _stream()),
                 "pgw_time_mean_f32")
         # the pipelines run on their own streams, which do not wait for the stream the arena was filled on
@@ -135,28 +136,51 @@ class DeltaSet:
         return [self.arena]
 
     def bracket(self, name, when):
-        key = (name, when)
+        """TimeBracket of variable ``name`` for the ERA5 date ``when``; variables that share their time axis
+        (normally all of them) share the result, and the year-shifted stamps are kept per year."""
+        gid = self._time_group.get(name)
+        if gid is None:
+            stamps = self.vars[name]["time"]
+            gid = self._time_group[name] = self._time_ids.setdefault(stamps.tobytes(), len(self._time_ids))
+        key = (gid, when)
         b = self._brackets.get(key)
         if b is None:
             if len(self._brackets) > 4096:
                 self._brackets.clear()
-            b = timeinterp.bracket(self.vars[name]["time"], when)
+            stamps = self.vars[name]["time"]
+            mk = (gid, when.year)
+            moved = self._moved.get(mk)
+            if moved is None:
+                if len(self._moved) > 64:
+                    self._moved.clear()
+                moved = self._moved[mk] = timeinterp.moved_to_year(stamps, when.year)
+            b = timeinterp.bracket(stamps, when, moved=moved)
             self._brackets[key] = b
         return b
+
+    def _layout(self, name):
+        """(address of the first time slab, bytes per time slab, bytes per level) of a variable."""
+        lay = self._lay.get(name)
+        if lay is None:
+            t = self.d4 if name == "d4" else self.vars[name]["data"]
+            lay = (t.data_ptr(), t.stride(0) * 4, (t.stride(1) * 4) if t.dim() == 4 else 0)
+            self._lay[name] = lay
+        return lay
 
     def slab(self, name, when, level=None):
         """pgw_tslab for variable ``name`` at ERA5 time ``when`` (optionally one plev)."""
         b = self.bracket(name, when)
-        data = self.vars[name]["data"]
-        lo, hi = data[b.ind_before], data[b.ind_after]
-        if level is not None:
-            lo, hi = lo[level], hi[level]
-        return N.TSlab(lo.data_ptr(), hi.data_ptr(), b.x_hi, b.x_new)
+        base, st, sl = self._layout(name)
+        off = base + (sl * level if level is not None else 0)
+        nt = len(self.vars[name]["time"])
+        return N.TSlab(off + st * (b.ind_before % nt), off + st * (b.ind_after % nt), b.x_hi, b.x_new)
 
     def slab4(self, when):
         """pgw_tslab of the packed (ta, hur, ua, va) deltas at ERA5 time ``when``."""
         b = self.bracket("ta", when)
-        return N.TSlab(self.d4[b.ind_before].data_ptr(), self.d4[b.ind_after].data_ptr(), b.x_hi, b.x_new)
+        base, st, _ = self._layout("d4")
+        nt = len(self.vars["ta"]["time"])
+        return N.TSlab(base + st * (b.ind_before % nt), base + st * (b.ind_after % nt), b.x_hi, b.x_new)
 
 
 class Pending:
@@ -217,6 +241,7 @@ class PGWEngine:
         self.k_pred = 8
         self._n_hist = []               # iteration counts of the last few timesteps
         self._ws = {}
+        self._zg_level = {}
         self.stats = dict(timesteps=0, rewrites=0, reruns=0, launches=0)
         self.kernel_events = None       # set to [] to collect CUDA events around the column kernel
 
@@ -288,7 +313,8 @@ class PGWEngine:
         self.stats["launches"] += 4
         ws["event"].record()
         ctx = dict(era=era, when=era_step_dt, ignore_top=ignore_top_pressure_error, k_spec=k_spec,
-                   k_max=k_max, keep=(f, a), file_name=file_name, slot=slot, direct=direct)
+                   k_max=k_max, keep=(f, a), file_name=file_name, slot=slot, direct=direct,
+                   stream=torch.cuda.current_stream())
         p = Pending(self, a, out, ws, ctx)
         ws["inflight"] = p
         return p
@@ -323,56 +349,66 @@ class PGWEngine:
             k_spec = self.k_pred
         k_spec = max(1, min(int(k_spec), k_max))
         ws = self._workspace(ncol, k_max, slot)
-        status = ws["status"]
 
         zg = ds.vars["zg"]
         if settings.p_ref_inp is None:                                    # staged path: level picked per column
-            sel, p_ref_scalar = [0], float(zg["plev"][0])
+            sel0, p_ref_scalar = 0, float(zg["plev"][0])
         else:
             p_ref_scalar = float(settings.p_ref_inp)
-            sel = np.nonzero(zg["plev"] == p_ref_scalar)[0]               # .sel(plev=p_ref), step_03:294
-            if len(sel) != 1:
-                raise KeyError(p_ref_scalar)
+            sel0 = self._zg_level.get(p_ref_scalar)
+            if sel0 is None:
+                sel = np.nonzero(zg["plev"] == p_ref_scalar)[0]           # .sel(plev=p_ref), step_03:294
+                if len(sel) != 1:
+                    raise KeyError(p_ref_scalar)
+                sel0 = self._zg_level[p_ref_scalar] = int(sel[0])
 
-        a = N.TimestepArgs()
-        a.ncol, a.nlev, a.nplev, a.nsoil = ncol, L, len(ds.plev), nsoil
-        a.plev_descending = int(ds.plev_descending)
-        a.ak, a.bk, a.akm, a.bkm = (self.ak_d.data_ptr(), self.bk_d.data_ptr(), self.akm_d.data_ptr(),
-                                    self.bkm_d.data_ptr())
-        a.plev = ds.plev_dev.data_ptr()
-        a.ak_host, a.bk_host = self.ak.ctypes.data, self.bk.ctypes.data
-        a.akm_host, a.bkm_host = self.akm.ctypes.data, self.bkm.ctypes.data
-        for name in ("PS", "FIS", "FR_LAND", "FR_SEA_ICE", "T_SKIN", "T", "QV", "U", "V"):
-            setattr(a, name, f[name].data_ptr())
-        a.T_SO = f["T_SO"].data_ptr() if nsoil else 0
+        # everything that does not change from one timestep to the next on this slot is filled once
+        in_names = ("PS", "FIS", "FR_LAND", "FR_SEA_ICE", "T_SKIN", "T", "QV", "U", "V")
+        out_names = ("PS", "T_SKIN", "FR_SEA_ICE", "T", "QV", "U", "V")
+        key = (tuple(f[n].data_ptr() for n in in_names), f["T_SO"].data_ptr() if nsoil else 0,
+               tuple(out[n].data_ptr() for n in out_names), out["T_SO"].data_ptr() if nsoil else 0,
+               out["delta_ps"].data_ptr(), ncol)
+        if ws.get("args_key") != key:
+            t = N.TimestepArgs()
+            t.ncol, t.nlev, t.nplev, t.nsoil = ncol, L, len(ds.plev), nsoil
+            t.plev_descending = int(ds.plev_descending)
+            t.ak, t.bk, t.akm, t.bkm = (self.ak_d.data_ptr(), self.bk_d.data_ptr(), self.akm_d.data_ptr(),
+                                        self.bkm_d.data_ptr())
+            t.plev = ds.plev_dev.data_ptr()
+            t.ak_host, t.bk_host = self.ak.ctypes.data, self.bk.ctypes.data
+            t.akm_host, t.bkm_host = self.akm.ctypes.data, self.bkm.ctypes.data
+            for name in in_names:
+                setattr(t, name, f[name].data_ptr())
+            t.T_SO = f["T_SO"].data_ptr() if nsoil else 0
+            t.ts_clim = ds.ts_clim.data_ptr()
+            for i, v in enumerate(self.soil_decay):
+                t.soil_decay[i] = float(v)
+            t.PS_out, t.T_SKIN_out, t.FR_SEA_ICE_out = (out["PS"].data_ptr(), out["T_SKIN"].data_ptr(),
+                                                        out["FR_SEA_ICE"].data_ptr())
+            t.T_SO_out = out["T_SO"].data_ptr() if nsoil else 0
+            t.T_out, t.QV_out, t.U_out, t.V_out = (out["T"].data_ptr(), out["QV"].data_ptr(),
+                                                   out["U"].data_ptr(), out["V"].data_ptr())
+            t.dps_out = out["delta_ps"].data_ptr()
+            t.dps_traj = ws["traj"].data_ptr()
+            base = ws["status"].data_ptr()
+            S = N.TimestepStatus
+            t.maxerr = base + S.maxerr.offset
+            t.stats = base + S.stats.offset
+            t.err = base + S.err.offset
+            t.first_k = base + S.first_k.offset
+            t.poly_fallback = base + S.poly_fallback.offset
+            ws["args_key"], ws["args"] = key, t
+        a = N.TimestepArgs.from_buffer_copy(ws["args"])
         a.d4 = ds.slab4(era_step_dt)
         for name in ("tas", "hurs", "ps_hist", "ts", "tos", "siconc"):
             setattr(a, name, ds.slab(name, era_step_dt))
-        a.zg_ref = ds.slab("zg", era_step_dt, level=int(sel[0]))
-        a.ts_clim = ds.ts_clim.data_ptr()
-        for i, v in enumerate(self.soil_decay):
-            a.soil_decay[i] = float(v)
+        a.zg_ref = ds.slab("zg", era_step_dt, level=sel0)
         a.p_ref = p_ref_scalar
         a.adj_factor = float(settings.adj_factor)
         a.thresh_phi_ref_max_error = float(settings.thresh_phi_ref_max_error)
         a.k_spec = k_spec
         a.ps_bound = self.ps_bound
-        a.PS_out, a.T_SKIN_out, a.FR_SEA_ICE_out = (out["PS"].data_ptr(), out["T_SKIN"].data_ptr(),
-                                                    out["FR_SEA_ICE"].data_ptr())
-        a.T_SO_out = out["T_SO"].data_ptr() if nsoil else 0
-        a.T_out, a.QV_out, a.U_out, a.V_out = (out["T"].data_ptr(), out["QV"].data_ptr(),
-                                               out["U"].data_ptr(), out["V"].data_ptr())
-        a.dps_out = out["delta_ps"].data_ptr()
-        a.dps_traj = ws["traj"].data_ptr()
-        base = status.data_ptr()
-        S = N.TimestepStatus
-        a.maxerr = base + S.maxerr.offset
-        a.stats = base + S.stats.offset
-        a.err = base + S.err.offset
-        a.first_k = base + S.first_k.offset
-        a.poly_fallback = base + S.poly_fallback.offset
-        if getattr(settings, "i_reference_dtypes", 0):
-            a.flags |= N.FLAG_REF_DTYPES
+        a.flags = N.FLAG_REF_DTYPES if getattr(settings, "i_reference_dtypes", 0) else 0
         return a, f, out, ws, k_spec, k_max
 
     # ------------------------------------------------------------------ completion
@@ -400,14 +436,16 @@ class PGWEngine:
         if err & N.ERR_PS_BOUND:
             self.ps_bound *= 1.25
             self.stats["reruns"] += 1
-            return self.submit(ctx["era"], ctx["when"], out=p.out, ignore_top_pressure_error=ctx["ignore_top"],
+            with torch.cuda.stream(ctx["stream"]):       # a rerun goes where the timestep was submitted
+                return self.submit(ctx["era"], ctx["when"], out=p.out, ignore_top_pressure_error=ctx["ignore_top"],
                                k_spec=ctx["k_spec"], file_name=ctx["file_name"], slot=ctx["slot"],
                                direct=ctx["direct"]).result()
         if not converged:
             if ctx["k_spec"] >= ctx["k_max"]:
                 raise ValueError(MSG_NOCONV.format(ctx["file_name"]))   # step_03:315-319
             self.stats["reruns"] += 1
-            return self.submit(ctx["era"], ctx["when"], out=p.out, ignore_top_pressure_error=ctx["ignore_top"],
+            with torch.cuda.stream(ctx["stream"]):
+                return self.submit(ctx["era"], ctx["when"], out=p.out, ignore_top_pressure_error=ctx["ignore_top"],
                                k_spec=ctx["k_max"], file_name=ctx["file_name"], slot=ctx["slot"],
                                direct=ctx["direct"]).result()
         # predict the largest recent count: one iteration too many costs a cheap rewrite

@@ -175,10 +175,29 @@ _UNIT_SECONDS = {"second": 1.0, "seconds": 1.0, "sec": 1.0, "secs": 1.0, "s": 1.
                  "hr": 3600.0, "hrs": 3600.0, "h": 3600.0, "day": 86400.0, "days": 86400.0, "d": 86400.0}
 
 
+def _month_lengths(calendar, year):
+    """Days per month of ``year`` in a CF calendar that is not the proleptic Gregorian one."""
+    if calendar in ("noleap", "365_day"):
+        feb = 28
+    elif calendar in ("all_leap", "366_day"):
+        feb = 29
+    elif calendar == "360_day":
+        return [30] * 12
+    elif calendar == "julian":
+        feb = 29 if year % 4 == 0 else 28
+    else:
+        raise ValueError("unsupported calendar %r" % calendar)
+    return [31, feb, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31]
+
+
 def decode_time(var):
-    """CF time axis ('<unit> since <date>') -> numpy datetime64[ns].  Standard/gregorian,
-    proleptic_gregorian and noleap/365_day calendars are handled the way the reference ends up
-    with them after ``to_datetimeindex`` (functions.py:210-221): the calendar date is kept."""
+    """CF time axis ('<unit> since <date>') -> numpy datetime64[ns], the way the reference ends up with it after
+    ``xr.open_dataset`` + ``CFTimeIndex.to_datetimeindex()`` (functions.py:203-221): in a non-standard calendar
+    (noleap/365_day, all_leap/366_day, 360_day, julian) the stamp is counted in THAT calendar and its calendar
+    date (year, month, day, time of day) is kept; a date the standard calendar does not have (30 February of a
+    360_day file, 29 February of a non-leap year) raises ValueError, as ``to_datetimeindex`` does -- nothing is
+    ever shifted.  standard / gregorian / proleptic_gregorian use the proleptic Gregorian arithmetic of
+    ``datetime`` (identical for dates after 1582).  Any other calendar name raises ValueError."""
     units = str(var.attrs.get("units", ""))
     calendar = str(var.attrs.get("calendar", "standard")).lower()
     if np.issubdtype(var.data.dtype, np.datetime64):
@@ -191,30 +210,43 @@ def decode_time(var):
     parts = ref.split()
     date = parts[0].split("-")
     hms = (parts[1].split(":") if len(parts) > 1 else []) + ["0", "0", "0"]
-    origin = datetime(int(date[0]), int(date[1]), int(date[2]), int(hms[0]), int(hms[1]),
-                      int(float(hms[2])))
+    oy, om, od = int(date[0]), int(date[1]), int(date[2])
+    oh, omi, osec = int(hms[0]), int(hms[1]), int(float(hms[2]))
     secs = np.asarray(var.data, dtype=np.float64) * scale
     out = []
-    if calendar in ("noleap", "365_day"):
-        month_len = [31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31]
-        doy0 = sum(month_len[:origin.month - 1]) + origin.day - 1
-        base = origin.hour * 3600 + origin.minute * 60 + origin.second
-        for s in secs:
-            total = base + s
-            days = int(np.floor(total / 86400.0))
-            rem = total - days * 86400.0
-            day_abs = doy0 + days
-            year = origin.year + day_abs // 365
-            doy = day_abs % 365
-            m = 0
-            while doy >= month_len[m]:
-                doy -= month_len[m]
-                m += 1
-            out.append(np.datetime64(datetime(year, m + 1, doy + 1) + timedelta(seconds=float(rem)), "ns"))
-    else:
+    if calendar in ("standard", "gregorian", "proleptic_gregorian"):
+        origin = datetime(oy, om, od, oh, omi, osec)
         for s in secs:
             out.append(np.datetime64(origin + timedelta(seconds=float(s)), "ns"))
-    return np.array(out, dtype="datetime64[ns]")
+        return np.array(out, dtype="datetime64[ns]")
+    ml0 = _month_lengths(calendar, oy)               # raises for an unknown calendar
+    if not (1 <= om <= 12 and 1 <= od <= ml0[om - 1]):
+        raise ValueError("reference date %s does not exist in calendar %s" % (parts[0], calendar))
+    base = oh * 3600 + omi * 60 + osec
+    for s in np.atleast_1d(secs):
+        total = base + float(s)
+        days = int(np.floor(total / 86400.0))
+        rem = total - days * 86400.0
+        year = oy
+        doy = sum(ml0[:om - 1]) + od - 1 + days      # day of `year`, may lie outside it
+        while doy < 0:
+            year -= 1
+            doy += sum(_month_lengths(calendar, year))
+        while doy >= sum(_month_lengths(calendar, year)):
+            doy -= sum(_month_lengths(calendar, year))
+            year += 1
+        ml = _month_lengths(calendar, year)
+        m = 0
+        while doy >= ml[m]:
+            doy -= ml[m]
+            m += 1
+        try:
+            stamp = datetime(year, m + 1, doy + 1)
+        except ValueError:
+            raise ValueError("Cannot convert date %04d-%02d-%02d of calendar %s to a date that is valid in the "
+                             "standard calendar" % (year, m + 1, doy + 1, calendar))
+        out.append(np.datetime64(stamp + timedelta(seconds=float(rem)), "ns"))
+    return np.array(out, dtype="datetime64[ns]").reshape(np.shape(secs))
 
 
 def encode_time(stamps, units="seconds since 1970-01-01 00:00:00"):

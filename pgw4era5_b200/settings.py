@@ -74,6 +74,12 @@ i_reinterp = 0
 #   1: reproduce the float32 rounding steps of the reference exactly where it applies them.
 i_reference_dtypes = 0
 
+# Not in the reference's settings.py.  The reference replaces PS, T, QV, U, V by its float64 PGW state and
+# to_netcdf writes them as float64 (step_03_apply_to_era.py:367-381) although the ERA5 file holds float32.
+#   0 (default): written in the dtype of the input file (half the bytes; files stay NetCDF-3 raw-pipeline capable)
+#   1: float64 like the reference, for users who diff outputs against a reference run
+i_reference_output_dtypes = 0
+
 
 def _load_user_settings():
     path = _os.environ.get('PGW_SETTINGS')

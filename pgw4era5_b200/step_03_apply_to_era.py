@@ -104,8 +104,8 @@ def pgw_for_era5(inp_era_file_path, out_era_file_path, delta_input_dir, era_step
     else:                                                                      # step_03:367-381
         for key in ("PS", "T", "QV", "U", "V", "T_SKIN", "T_SO", "FR_SEA_ICE"):
             ref = era_file[names[key]]
-            era_file[names[key]] = ncio.Variable(ref.dims, host[key].reshape(ref.data.shape).astype(ref.data.dtype),
-                                                 ref.attrs)
+            era_file[names[key]] = ncio.Variable(
+                ref.dims, host[key].reshape(ref.data.shape).astype(_out_dtype(key, ref.data.dtype)), ref.attrs)
         if vmap['hur'] in era_file:
             del era_file[vmap['hur']]
         era_file.to_netcdf(out_era_file_path, mode='w')
@@ -121,6 +121,17 @@ _ERA_NAMES = lambda vmap: dict(PS=vmap['ps'], FIS=vmap['zgs'], FR_LAND=vmap['sft
 
 
 _WRITTEN = ("PS", "T", "QV", "U", "V", "T_SKIN", "T_SO", "FR_SEA_ICE")
+# The reference replaces PS, T, QV, U, V by its float64 PGW state and to_netcdf keeps that dtype
+# (step_03_apply_to_era.py:367-381); skin, soil and sea ice are updated in place and keep the file's dtype.
+_F64_IN_REFERENCE = ("PS", "T", "QV", "U", "V")
+
+
+def _out_dtype(key, file_dtype):
+    """dtype a written field gets: the input file's (default, half the bytes of the reference's files), or
+    with ``settings.i_reference_output_dtypes = 1`` float64 for the five fields the reference writes as float64."""
+    if getattr(settings, "i_reference_output_dtypes", 0) and key in _F64_IN_REFERENCE:
+        return np.float64
+    return file_dtype
 IO_STATS = {"raw": 0, "decoded": 0}          # files per I/O path of pgw_for_era5_files (tests, bench_files.py)
 
 
@@ -129,8 +140,8 @@ def _raw_layout(path, names, host_in):
     record at most, every ERA5 field float32 with the size of its host buffer, no RELHUM to drop
     (step_03:371).  Else None (the decoding path is taken)."""
     from .nc3raw import NC_FLOAT, NotNetCDF3, RawNC3
-    if os.environ.get("PGW_RAW_IO", "1") == "0":
-        return None
+    if os.environ.get("PGW_RAW_IO", "1") == "0" or getattr(settings, "i_reference_output_dtypes", 0):
+        return None                 # float64 outputs change the layout of the file: decoding path
     try:
         raw = RawNC3(path)
     except (NotNetCDF3, OSError):
@@ -228,6 +239,25 @@ def pgw_for_era5_files(steps, delta_input_dir, ignore_top_pressure_error, debug_
         free_out.put(pipe.alloc_host_outputs())
     loaded, to_write = queue.Queue(maxsize=n_in_buf), queue.Queue()
     failure = []
+    stop = threading.Event()         # set on any failure (or at the end): every blocking get/put below polls it
+
+    def q_get(q):
+        """q.get() that gives up (returns None) once the pipeline has been stopped."""
+        while True:
+            try:
+                return q.get(timeout=0.2)
+            except queue.Empty:
+                if stop.is_set():
+                    return None
+
+    def q_put(q, item):
+        while True:
+            try:
+                q.put(item, timeout=0.2)
+                return True
+            except queue.Full:
+                if stop.is_set():
+                    return False
     # the raw path is a copy between the page cache and pinned memory: a few threads per direction
     # (pread / pwrite release the GIL) move the fields of one file side by side
     n_io = max(1, min(4, (os.cpu_count() or 2) // 2))
@@ -238,7 +268,9 @@ def pgw_for_era5_files(steps, delta_input_dir, ignore_top_pressure_error, debug_
             for k, st in enumerate(steps):
                 if settings.i_debug >= 0:
                     print('Start working on input file {}'.format(st["inp_era_file_path"]))
-                h = free_in.get()
+                h = q_get(free_in)
+                if h is None:
+                    return
                 raw = _raw_layout(st["inp_era_file_path"], names, h)
                 if raw is not None and os.path.realpath(st["inp_era_file_path"]) != \
                         os.path.realpath(st["out_era_file_path"]):
@@ -246,17 +278,20 @@ def pgw_for_era5_files(steps, delta_input_dir, ignore_top_pressure_error, debug_
                         for fut in [rpool.submit(raw.read_into, f, names[key], h[key].numpy()) for key in IN_FIELDS]:
                             fut.result()
                     IO_STATS["raw"] += 1
-                    loaded.put((st, raw, h))
+                    if not q_put(loaded, (st, raw, h)):
+                        return
                     continue
                 IO_STATS["decoded"] += 1
                 era_file = first if k == 0 else ncio.open_dataset(st["inp_era_file_path"], decode_cf=False)
                 for key in IN_FIELDS:
                     h[key].numpy()[...] = np.asarray(era_file[names[key]].data, dtype=np.float32).reshape(h[key].shape)
-                loaded.put((st, era_file, h))
+                if not q_put(loaded, (st, era_file, h)):
+                    return
         except BaseException as e:          # surfaced by the main thread
             failure.append(e)
+            stop.set()
         finally:
-            loaded.put(None)
+            q_put(loaded, None)
 
     def writer():
         try:
@@ -274,7 +309,8 @@ def pgw_for_era5_files(steps, delta_input_dir, ignore_top_pressure_error, debug_
                 for key in _WRITTEN:
                     ref = era_file[names[key]]
                     era_file[names[key]] = ncio.Variable(
-                        ref.dims, host[key].numpy().reshape(ref.data.shape).astype(ref.data.dtype), ref.attrs)
+                        ref.dims, host[key].numpy().reshape(ref.data.shape).astype(_out_dtype(key, ref.data.dtype)),
+                        ref.attrs)
                 if vmap['hur'] in era_file:
                     del era_file[vmap['hur']]
                 era_file.to_netcdf(st["out_era_file_path"], mode='w')
@@ -283,7 +319,10 @@ def pgw_for_era5_files(steps, delta_input_dir, ignore_top_pressure_error, debug_
                 if settings.i_debug >= 1:
                     print('Done. Saved to file {}.'.format(st["out_era_file_path"]))
         except BaseException as e:
+            # disk full, permission, to_netcdf error ...: the main thread must not keep waiting for the output
+            # buffers only this thread hands back
             failure.append(e)
+            stop.set()
 
     tr, tw = threading.Thread(target=reader, daemon=True), threading.Thread(target=writer, daemon=True)
     tr.start(); tw.start()
@@ -297,22 +336,30 @@ def pgw_for_era5_files(steps, delta_input_dir, ignore_top_pressure_error, debug_
 
     try:
         while True:
-            item = loaded.get()
+            item = q_get(loaded)
             if item is None:
                 break
             st, era_file, h_in = item
-            h_out = free_out.get()
+            h_out = q_get(free_out)
+            if h_out is None:
+                break
             done = pipe.run(h_in, st["era_step_dt"], h_out, raw=not isinstance(era_file, ncio.Dataset),
                             ignore_top_pressure_error=ignore_top_pressure_error, file_name=st["inp_era_file_path"])
             in_flight.append((st, era_file, h_in, h_out))
             if done is not None:
                 retire(done)
-        for done in pipe.drain():
-            if done is not None:
-                retire(done)
+        if not stop.is_set():
+            for done in pipe.drain():
+                if done is not None:
+                    retire(done)
+    except BaseException:
+        stop.set()                   # the reader must not stay blocked on its queues
+        raise
     finally:
         to_write.put(None)
         tw.join()
+        stop.set()
+        tr.join(timeout=5)
         rpool.shutdown(wait=False)
         wpool.shutdown(wait=False)
     if failure:

@@ -42,7 +42,12 @@ class TimeBracket:
         return self.ind_before == self.ind_after
 
 
-def bracket(kept_stamps, target):
+def moved_to_year(kept_stamps, year):
+    """The stamps with their year replaced by ``year`` (functions.py:235-238)."""
+    return np.array([np.datetime64(to_datetime(s).replace(year=year), "ns") for s in kept_stamps])
+
+
+def bracket(kept_stamps, target, moved=None):
     """
     functions.py:233-292.  ``kept_stamps``: datetime64 stamps with 29 Feb already
     dropped; ``target``: naive ``datetime``.  Stamps are moved to the target's year;
@@ -50,7 +55,8 @@ def bracket(kept_stamps, target):
     the previous year (first stamp of the next year).
     """
     year = target.year
-    moved = np.array([np.datetime64(to_datetime(s).replace(year=year), "ns") for s in kept_stamps])
+    if moved is None:                  # callers that bracket many dates pass moved_to_year(kept_stamps, year)
+        moved = moved_to_year(kept_stamps, year)
     tgt = np.datetime64(target, "ns")
     before = np.nonzero(moved <= tgt)[0]
     after = np.nonzero(moved >= tgt)[0]

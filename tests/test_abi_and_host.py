@@ -188,3 +188,41 @@ def test_numa_binding_helpers():
     import torch
     if not torch.cuda.is_available():
         assert bind_to_gpu_numa(0) is None and os.sched_getaffinity(0) == before
+
+
+def test_decode_time_calendars():
+    """CF calendars the way the reference ends up with them after to_datetimeindex (functions.py:203-221): the
+    calendar date is kept, nothing is shifted; dates the standard calendar lacks and unknown calendars raise."""
+    from pgw4era5_b200 import ncio, timeinterp
+    V = ncio.Variable
+    # a 360_day monthly delta file (HadGEM / UKESM style): mid-month stamps of model year 2000
+    t360 = np.array([150 * 360 + 30 * m + 15.5 for m in range(12)])
+    got = ncio.decode_time(V(("time",), t360, {"units": "days since 1850-01-01", "calendar": "360_day"}))
+    want = np.array(["2000-%02d-16T12:00:00" % (m + 1) for m in range(12)], dtype="datetime64[ns]")
+    assert np.array_equal(got, want)
+    # ... which brackets an ERA5 date exactly like a standard-calendar file with the same stamps
+    from datetime import datetime
+    b = timeinterp.bracket(got, datetime(2006, 8, 2, 6))
+    assert (b.ind_before, b.ind_after) == (6, 7)
+    # decoded as proleptic Gregorian (what the code did before) these stamps would drift ~5 days per year
+    greg = ncio.decode_time(V(("time",), t360, {"units": "days since 1850-01-01"}))
+    assert abs((greg[0] - want[0]) / np.timedelta64(1, "D")) > 700
+    # noleap across years, all_leap, julian
+    got = ncio.decode_time(V(("time",), np.array([59.5, 365.0 + 59.5]),
+                             {"units": "days since 2001-01-01", "calendar": "noleap"}))
+    assert np.array_equal(got, np.array(["2001-03-01T12", "2002-03-01T12"], dtype="datetime64[ns]"))
+    got = ncio.decode_time(V(("time",), np.array([60.0, 366.0 + 60.0]),
+                             {"units": "days since 2000-01-01", "calendar": "366_day"}))
+    assert np.array_equal(got, np.array(["2000-03-01", "2001-03-01"], dtype="datetime64[ns]"))
+    # 1900-02-29 exists in the julian calendar only
+    with pytest.raises(ValueError, match="standard calendar"):
+        ncio.decode_time(V(("time",), np.array([365.0 * 3 + 59.0]),
+                           {"units": "days since 1897-01-01", "calendar": "julian"}))
+    with pytest.raises(ValueError, match="standard calendar"):          # 30 February
+        ncio.decode_time(V(("time",), np.array([150 * 360 + 59.0]), {"units": "days since 1850-01-01",
+                                                                     "calendar": "360_day"}))
+    with pytest.raises(ValueError, match="unsupported calendar"):
+        ncio.decode_time(V(("time",), np.array([1.0]), {"units": "days since 1850-01-01", "calendar": "lunar"}))
+    # negative offsets
+    got = ncio.decode_time(V(("time",), np.array([-1.0]), {"units": "days since 2001-01-01", "calendar": "360_day"}))
+    assert got[0] == np.datetime64("2000-12-30")

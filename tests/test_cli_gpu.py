@@ -257,3 +257,69 @@ def test_extpar_adapt(tmp_path):
     got = ncio.open_dataset(str(tmp_path / "extpar.nc"))["T_CL"].data
     ts = np.asarray(S.to_numpy(deltas)["ts"]["data"], dtype=np.float64)
     np.testing.assert_allclose(got, t_cl + ts.mean(axis=0), rtol=0, atol=1e-4)
+
+
+def _several_files(tmp_path, n, seed=53):
+    from datetime import timedelta
+    t0 = datetime(2006, 8, 2, 0)
+    inp, dd = tmp_path / "in", tmp_path / "deltas"
+    for p in (inp, dd):
+        p.mkdir()
+    era0, deltas = make_case(12, 20, seed)
+    _write_deltas(str(dd), deltas, era0["lat"], era0["lon"])
+    whens = [t0 + timedelta(hours=6 * i) for i in range(n)]
+    for i, when in enumerate(whens):
+        era = S.make_era5(12, 20, 10 * seed + i, lat=era0["lat"], lon=era0["lon"], orog_seed=seed)
+        _write_era(str(inp / settings.era5_file_name_base.format(when)), era, when)
+    return inp, dd, whens
+
+
+@pytest.mark.timeout(120)
+def test_step_03_pipeline_surfaces_writer_failure(tmp_path):
+    """Seven files into an output directory that does not exist: the writer thread fails on the first one.
+    With only four output buffers in circulation (handed back by the writer alone) the main loop used to block
+    for ever; now the error comes out and the reader thread ends too."""
+    import threading
+    from pgw4era5_b200 import step_03_apply_to_era as S3
+    inp, dd, whens = _several_files(tmp_path, 7)
+    steps = [dict(inp_era_file_path=str(inp / settings.era5_file_name_base.format(w)),
+                  out_era_file_path=str(tmp_path / "no_such_dir" / settings.era5_file_name_base.format(w)),
+                  era_step_dt=w) for w in whens]
+    old = settings.i_debug
+    settings.i_debug = -1
+    before = threading.active_count()
+    try:
+        with pytest.raises((OSError, IOError)):
+            S3.pgw_for_era5_files(steps, str(dd), True)
+    finally:
+        settings.i_debug = old
+    import time
+    time.sleep(0.6)
+    assert threading.active_count() <= before + 8       # reader and writer gone (only pool threads may linger)
+
+
+def test_step_03_reference_output_dtypes(tmp_path):
+    """settings.i_reference_output_dtypes = 1: PS, T, QV, U, V are written as float64 like the reference's
+    to_netcdf does (step_03_apply_to_era.py:367-381); skin, soil and sea ice keep the file's dtype; values are
+    the float32 results widened."""
+    from pgw4era5_b200 import step_03_apply_to_era as S3
+    inp, dd, whens = _several_files(tmp_path, 2, seed=54)
+    args = ["-i", str(inp), "-d", str(dd), "-f", "2006080200", "-l", "2006080206", "-H", "6", "-t"]
+    old = settings.i_debug, settings.i_reference_output_dtypes
+    settings.i_debug = -1
+    try:
+        S3.main(args + ["-o", str(tmp_path / "out32")])
+        settings.i_reference_output_dtypes = 1
+        S3.main(args + ["-o", str(tmp_path / "out64")])
+    finally:
+        settings.i_debug, settings.i_reference_output_dtypes = old
+    for w in whens:
+        name = settings.era5_file_name_base.format(w)
+        a, b = ncio.open_dataset(str(tmp_path / "out32" / name)), ncio.open_dataset(str(tmp_path / "out64" / name))
+        for key in ("PS", "T", "QV", "U", "V"):
+            assert a[key].data.dtype == np.float32 and b[key].data.dtype == np.float64, key
+            tol = 5e-9 if key == "QV" else 0.0          # k_spec history differs between the two runs (rewrite path)
+            np.testing.assert_allclose(b[key].data, a[key].data.astype(np.float64), rtol=0, atol=tol)
+        for key in ("T_SKIN", "T_SO", "FR_SEA_ICE"):
+            assert b[key].data.dtype == np.float32
+            np.testing.assert_array_equal(a[key].data, b[key].data)
