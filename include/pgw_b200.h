@@ -362,6 +362,15 @@ int pgw_regrid_bilinear_f32(const float *src, float *dst, const float *polemean,
                             const int *j0, const int *j1, const double *wy,
                             const int *i0, const int *i1, const double *wx,
                             void *stream);
+/* The same for the band [jt_begin, jt_end) of target rows only; dst holds just those rows,
+ * [nfield, jt_end - jt_begin, nx_t].  One variable split over several GPUs by target latitude (the source field
+ * is replicated, the pole-row means are computed on every GPU); the tables stay those of the whole target grid. */
+int pgw_regrid_bilinear_band_f32(const float *src, float *dst, const float *polemean,
+                                 long long nfield, int ny_s, int nx_s, int ny_t, int nx_t,
+                                 int jt_begin, int jt_end,
+                                 const int *j0, const int *j1, const double *wy,
+                                 const int *i0, const int *i1, const double *wx,
+                                 void *stream);
 int pgw_smooth_harmonic_f32(const float *series, float *out, int nt, long long npoint,
                             void *stream);
 

@@ -115,6 +115,7 @@ def _load():
         "pgw_band_unpack": (i, [vp, vp, vp]),
         "pgw_zonal_mean_f32": (i, [vp, vp, ll, i, i, vp]),
         "pgw_regrid_bilinear_f32": (i, [vp, vp, vp, ll, i, i, i, i, vp, vp, vp, vp, vp, vp, vp]),
+        "pgw_regrid_bilinear_band_f32": (i, [vp, vp, vp, ll, i, i, i, i, i, i, vp, vp, vp, vp, vp, vp, vp]),
         "pgw_smooth_harmonic_f32": (i, [vp, vp, i, ll, vp]),
         "pgw_surface_update": (i, [C.POINTER(TimestepArgs), vp]),
         "pgw_hybrid_pressure_f64": (i, [vp, vp, vp, vp, i, ll, vp]),

@@ -6,6 +6,12 @@
 // smoothing reads and writes every series once.
 #include "pgw_common.cuh"
 
+#include <limits.h>
+#include <stdlib.h>
+#include <string.h>
+
+int pgw_ensure_smem(const void *kernel, int slot, size_t smem, int np);
+
 namespace pgw {
 
 // zonal mean of the first and last source row of every field: the values the
@@ -159,6 +165,147 @@ regrid_rows_kernel(const float *__restrict__ src, float *__restrict__ dst, const
     }
 }
 
+// Walking variant (the production path for ERA5-sized targets): a CTA takes CHUNKS of kRegridChunk consecutive
+// target rows of one field.  (1) The few source rows the chunk needs (its rows j0..j1 span ~ chunk/4 + 2 rows of
+// a 1 degree source) are fetched ONCE with coalesced loads -- into registers while the previous chunk is being
+// computed, then parked in shared memory -- instead of four scattered gathers per thread and row pair; pole
+// rows (-1 / -2) read the zonal mean.  (2) Per pair of target rows the two bracketing source rows are blended
+// in latitude once per source column into shared memory (functions.py:859, float64), (3) every thread produces
+// VEC adjacent target longitudes of both rows (:892) and writes one 16-byte streaming store per row.  The
+// VEC targets of a thread touch at most three distinct source columns when source and target grids are
+// regular, so three shared-memory loads serve all of them (checked once per launch, else 2 VEC loads).
+// Same expressions as regrid_kernel, hence bit-identical.  `jt_begin, jt_end`: the band of target rows this
+// launch produces (dst holds only those rows): several GPUs split one variable by target latitude.
+constexpr int kRegridChunk = 8;        // target rows per chunk (even)
+constexpr int kRegridSrcRows = 6;      // source rows a chunk may span on the staged path
+
+template <int VEC>
+__global__ void __launch_bounds__(384, 3)
+regrid_walk_kernel(const float *__restrict__ src, float *__restrict__ dst, const float *__restrict__ polemean,
+                   int nfield, int ny_s, int nx_s, int nx_t, int jt_begin, int jt_end,
+                   const int *__restrict__ j0, const int *__restrict__ j1, const double *__restrict__ wy,
+                   const int *__restrict__ i0, const int *__restrict__ i1, const double *__restrict__ wx) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int nrow = jt_end - jt_begin, nchunk = (nrow + kRegridChunk - 1) / kRegridChunk;
+    double2 *const s_row = reinterpret_cast<double2 *>(smem_raw);                       // [2][nx_s]
+    float *const s_src = reinterpret_cast<float *>(s_row + 2 * nx_s);                     // [2][kRegridSrcRows][nx_s]
+    int2 *const s_chunk = reinterpret_cast<int2 *>(s_src + 2 * kRegridSrcRows * nx_s);    // [nchunk] (jmin, span)
+    const int tid = threadIdx.x;
+    const int nxv = nx_t / VEC;
+    const bool owner = tid < nxv;
+
+    // ---- per launch: span of source rows of every chunk; longitude brackets of this thread
+    for (int c = tid; c < nchunk; c += blockDim.x) {
+        int lo = INT_MAX, hi = -1;
+        for (int r = 0; r < kRegridChunk; ++r) {
+            const int jt = jt_begin + c * kRegridChunk + r;
+            if (jt >= jt_end) break;
+            const int a = j0[jt], b = j1[jt];
+            if (a >= 0) { lo = min(lo, a); hi = max(hi, a); }
+            if (b >= 0) { lo = min(lo, b); hi = max(hi, b); }
+        }
+        s_chunk[c] = hi < 0 ? make_int2(0, 0) : make_int2(lo, hi - lo + 1);
+    }
+    int ia[VEC], ib[VEC];
+    double w[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+        const int it = owner ? tid * VEC + v : 0;
+        ia[v] = i0[it]; ib[v] = i1[it]; w[v] = wx[it];
+    }
+    // three-column pattern: the first n1 targets bracket (u0, u1), the rest (u1, u2)
+    const int u0 = ia[0], u1 = ib[0], u2 = ib[VEC - 1];
+    int n1 = 0;
+    bool pat = true;
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+        const bool first = ia[v] == u0 && ib[v] == u1, second = ia[v] == u1 && ib[v] == u2;
+        if (first && n1 == v) n1 = v + 1;
+        else if (!second) pat = false;
+    }
+    const bool three = __syncthreads_and(pat || !owner) != 0;       // also publishes s_chunk
+
+    const int nitem = nfield * nchunk;
+    float reg[kRegridSrcRows];
+    auto prefetch = [&](int item) {
+        if (item >= nitem || tid >= nx_s) return;
+        const int f = item / nchunk, c = item - f * nchunk;
+        const int2 ch = s_chunk[c];
+        if (ch.y > kRegridSrcRows) return;
+        const float *base = src + ((size_t)f * ny_s + ch.x) * (size_t)nx_s + tid;
+#pragma unroll
+        for (int r = 0; r < kRegridSrcRows; ++r)
+            if (r < ch.y) reg[r] = __ldg(base + (size_t)r * nx_s);
+    };
+    int item = blockIdx.x, buf = 0, pb = 0;
+    prefetch(item);
+    for (; item < nitem; item += gridDim.x, buf ^= 1) {
+        const int f = item / nchunk, c = item - f * nchunk;
+        const int2 ch = s_chunk[c];
+        const bool staged = ch.y <= kRegridSrcRows;
+        float *const ssrc = s_src + buf * kRegridSrcRows * nx_s;
+        if (staged && tid < nx_s) {
+#pragma unroll
+            for (int r = 0; r < kRegridSrcRows; ++r)
+                if (r < ch.y) ssrc[r * nx_s + tid] = reg[r];
+        }
+        prefetch(item + gridDim.x);                 // in flight while this chunk is computed
+        const float pm0 = __ldg(polemean + 2 * f), pm1 = __ldg(polemean + 2 * f + 1);
+        const float *const fld = src + (size_t)f * ny_s * (size_t)nx_s;
+        const int r_begin = c * kRegridChunk, r_end = min(r_begin + kRegridChunk, nrow);
+        // the parked rows become visible at the first barrier below
+        for (int r = r_begin; r < r_end; r += 2, pb ^= 1) {
+            const int jt0 = jt_begin + r, jt1 = min(jt0 + 1, jt_end - 1);
+            const bool two = r + 1 < r_end;
+            if (r == r_begin) __syncthreads();
+            double2 *const row = s_row + pb * nx_s;
+            if (tid < nx_s) {
+                auto at = [&](int j) -> double {
+                    if (j == -1) return (double)pm0;
+                    if (j == -2) return (double)pm1;
+                    return staged ? (double)ssrc[(j - ch.x) * nx_s + tid] : (double)__ldg(fld + (size_t)j * nx_s + tid);
+                };
+                const double a0 = at(j0[jt0]), a1 = at(j1[jt0]), c0 = at(j0[jt1]), c1 = at(j1[jt1]);
+                row[tid] = make_double2((a1 - a0) * wy[jt0] + a0, (c1 - c0) * wy[jt1] + c0);
+            }
+            __syncthreads();
+            if (owner) {
+                float r0[VEC], r1[VEC];
+                if (three) {
+                    const double2 q0 = row[u0], q1 = row[u1], q2 = row[u2];
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) {
+                        const bool fs = v < n1;
+                        const double ax = fs ? q0.x : q1.x, ay = fs ? q0.y : q1.y;
+                        const double bx = fs ? q1.x : q2.x, by = fs ? q1.y : q2.y;
+                        r0[v] = (float)((bx - ax) * w[v] + ax);
+                        r1[v] = (float)((by - ay) * w[v] + ay);
+                    }
+                } else {
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) {
+                        const double2 a = row[ia[v]], b = row[ib[v]];
+                        r0[v] = (float)((b.x - a.x) * w[v] + a.x);
+                        r1[v] = (float)((b.y - a.y) * w[v] + a.y);
+                    }
+                }
+                float *o0 = dst + ((size_t)f * nrow + r) * (size_t)nx_t + tid * VEC;
+                float *o1 = o0 + nx_t;
+                if (VEC == 4) {
+                    __stcs(reinterpret_cast<float4 *>(o0), make_float4(r0[0], r0[1], r0[2], r0[3]));
+                    if (two) __stcs(reinterpret_cast<float4 *>(o1), make_float4(r1[0], r1[1], r1[2], r1[3]));
+                } else {
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) {
+                        __stcs(o0 + v, r0[v]);
+                        if (two) __stcs(o1 + v, r1[v]);
+                    }
+                }
+            }
+        }
+    }
+}
+
 // harmonic_ac_analysis (functions.py:678-740): mean + harmonics 1..3 of an
 // nt-long series per grid point.  One thread per grid point, lanes = adjacent
 // points; cos/sin tables for the three harmonics are staged in shared memory.
@@ -213,13 +360,56 @@ int pgw_zonal_mean_f32(const float *src, float *polemean, long long nfield, int 
     return pgw_check_launch("zonal_mean_kernel");
 }
 
+int pgw_regrid_bilinear_band_f32(const float *src, float *dst, const float *polemean, long long nfield, int ny_s,
+                                 int nx_s, int ny_t, int nx_t, int jt_begin, int jt_end, const int *j0, const int *j1,
+                                 const double *wy, const int *i0, const int *i1, const double *wx, void *stream) {
+    if (!src || !dst || !polemean || !j0 || !j1 || !wy || !i0 || !i1 || !wx) return PGW_E_INVALID;
+    if (nfield <= 0 || ny_s < 1 || nx_s < 1 || ny_t < 1 || nx_t < 1) return PGW_E_INVALID;
+    if (jt_begin < 0 || jt_end > ny_t || jt_begin >= jt_end) return PGW_E_INVALID;
+    const int nrow = jt_end - jt_begin;
+    const bool vec = (nx_t % 4 == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+    const int nchunk = (nrow + kRegridChunk - 1) / kRegridChunk;
+    const char *force = getenv("PGW_REGRID_PATH");          // "rows" / "generic": the older kernels (A/B runs, tests)
+    const bool walk_ok = (vec ? nx_t / 4 : nx_t) <= 384 && nx_s <= 384 && nfield * (long long)nchunk < (1LL << 31) &&
+                         nchunk <= 4096 && !(force && (!strcmp(force, "rows") || !strcmp(force, "generic")));
+    if (walk_ok) {
+        const size_t smem = sizeof(double2) * 2 * (size_t)nx_s + sizeof(float) * 2 * kRegridSrcRows * (size_t)nx_s +
+                            sizeof(int2) * (size_t)nchunk;
+        const long long nitem = nfield * (long long)nchunk;
+        long long g = nitem < 148LL * 5 ? nitem : 148LL * 5;
+        if (smem > 48 * 1024) {
+            int rc;
+            if ((rc = pgw_ensure_smem(vec ? (const void *)regrid_walk_kernel<4> : (const void *)regrid_walk_kernel<1>,
+                                      vec ? 12 : 13, smem, 0)) != PGW_OK) return rc;
+        }
+        if (vec)
+            regrid_walk_kernel<4><<<(unsigned)g, 384, smem, (cudaStream_t)stream>>>(
+                src, dst, polemean, (int)nfield, ny_s, nx_s, nx_t, jt_begin, jt_end, j0, j1, wy, i0, i1, wx);
+        else
+            regrid_walk_kernel<1><<<(unsigned)g, 384, smem, (cudaStream_t)stream>>>(
+                src, dst, polemean, (int)nfield, ny_s, nx_s, nx_t, jt_begin, jt_end, j0, j1, wy, i0, i1, wx);
+        return pgw_check_launch("regrid_walk_kernel");
+    }
+    // the older kernels take whole grids only: shift the row tables and the destination
+    if (jt_begin != 0 || jt_end != ny_t)
+        return pgw_regrid_bilinear_f32(src, dst, polemean, nfield, ny_s, nx_s, nrow, nx_t, j0 + jt_begin, j1 + jt_begin,
+                                       wy + jt_begin, i0, i1, wx, stream);
+    return pgw_regrid_bilinear_f32(src, dst, polemean, nfield, ny_s, nx_s, ny_t, nx_t, j0, j1, wy, i0, i1, wx, stream);
+}
+
 int pgw_regrid_bilinear_f32(const float *src, float *dst, const float *polemean, long long nfield, int ny_s,
                             int nx_s, int ny_t, int nx_t, const int *j0, const int *j1, const double *wy,
                             const int *i0, const int *i1, const double *wx, void *stream) {
     if (!src || !dst || !polemean || !j0 || !j1 || !wy || !i0 || !i1 || !wx) return PGW_E_INVALID;
     if (nfield <= 0 || ny_s < 1 || nx_s < 1 || ny_t < 1 || nx_t < 1) return PGW_E_INVALID;
     const bool vec = (nx_t % 4 == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
-    if ((vec ? nx_t / 4 : nx_t) <= 384 && nx_s <= 384 && nfield * ny_s * (long long)nx_s < (1LL << 31)) {
+    const char *force = getenv("PGW_REGRID_PATH");
+    if (!(force && (!strcmp(force, "rows") || !strcmp(force, "generic"))) && (vec ? nx_t / 4 : nx_t) <= 384 &&
+        nx_s <= 384 && (ny_t + kRegridChunk - 1) / kRegridChunk <= 4096)
+        return pgw_regrid_bilinear_band_f32(src, dst, polemean, nfield, ny_s, nx_s, ny_t, nx_t, 0, ny_t, j0, j1, wy, i0,
+                                            i1, wx, stream);
+    if (!(force && !strcmp(force, "generic")) &&
+        (vec ? nx_t / 4 : nx_t) <= 384 && nx_s <= 384 && nfield * ny_s * (long long)nx_s < (1LL << 31)) {
         const long long nitem = nfield * (long long)((ny_t + 1) / 2);
         long long g = nitem < 148LL * 5 ? nitem : 148LL * 5;
         const size_t smem = sizeof(double) * 4 * (size_t)nx_s;

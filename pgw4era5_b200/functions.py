@@ -505,11 +505,14 @@ def regrid_tables(lat_gcm, lon_gcm, targ_lat, targ_lon):
                 i0=cols[ilo].astype(np.int32), i1=cols[ihi].astype(np.int32), wx=wx)
 
 
-def regrid_arrays(data, lat_gcm, lon_gcm, targ_lat, targ_lon):
+def regrid_arrays(data, lat_gcm, lon_gcm, targ_lat, targ_lon, rows=None):
     """
     regrid_lat_lon on arrays: data [..., nlat_gcm, nlon_gcm] -> [..., len(targ_lat),
     len(targ_lon)] float32.  Tables from ``regrid_tables``; the gather (latitude pass, then
-    longitude pass, float64 arithmetic) runs in pgw_regrid_bilinear_f32.
+    longitude pass, float64 arithmetic) runs in pgw_regrid_bilinear_band_f32.  ``rows = (r0, r1)``:
+    only that band of target rows is produced ([..., r1 - r0, len(targ_lon)]), bit-identical to the same
+    rows of the whole field -- one variable split over several GPUs by target latitude
+    (``parallel.regrid_banded``).
     """
     tb = regrid_tables(lat_gcm, lon_gcm, targ_lat, targ_lon)
     d = _dev(data, torch.float32)
@@ -522,13 +525,16 @@ def regrid_arrays(data, lat_gcm, lon_gcm, targ_lat, targ_lon):
     j0, j1, i0, i1 = ti(tb["j0"]), ti(tb["j1"]), ti(tb["i0"]), ti(tb["i1"])
     wyd, wxd = tf(tb["wy"]), tf(tb["wx"])
     ny_t, nx_t = len(tb["wy"]), len(tb["wx"])
+    r0, r1 = (0, ny_t) if rows is None else (int(rows[0]), int(rows[1]))
+    if not 0 <= r0 < r1 <= ny_t:
+        raise ValueError("rows %r outside the %d target rows" % (rows, ny_t))
     pm = torch.empty((nfield, 2), device=dev, dtype=torch.float32)
-    out = torch.empty(lead + (ny_t, nx_t), device=dev, dtype=torch.float32)
+    out = torch.empty(lead + (r1 - r0, nx_t), device=dev, dtype=torch.float32)
     st = _stream()
     N.check(N.lib.pgw_zonal_mean_f32(_p(d), _p(pm), nfield, ny_s, nx_s, st), "pgw_zonal_mean_f32")
-    N.check(N.lib.pgw_regrid_bilinear_f32(_p(d), _p(out), _p(pm), nfield, ny_s, nx_s, ny_t, nx_t,
-                                          _p(j0), _p(j1), _p(wyd), _p(i0), _p(i1), _p(wxd), st),
-            "pgw_regrid_bilinear_f32")
+    N.check(N.lib.pgw_regrid_bilinear_band_f32(_p(d), _p(out), _p(pm), nfield, ny_s, nx_s, ny_t, nx_t, r0, r1,
+                                               _p(j0), _p(j1), _p(wyd), _p(i0), _p(i1), _p(wxd), st),
+            "pgw_regrid_bilinear_band_f32")
     return _back(out, data)
 
 

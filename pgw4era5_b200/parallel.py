@@ -69,6 +69,55 @@ def broadcast_deltas(deltas, src=0, group=None, info=None):
     return ms
 
 
+def regrid_banded(data, lat_gcm, lon_gcm, targ_lat, targ_lon, group=None, src=0, gather=True, smooth=False,
+                  device=None, regrid_fn=None):
+    """
+    step_02 for ONE variable on all GPUs of ``group`` (third row): the source field on the GCM grid
+    is replicated (NCCL broadcast from ``src``: 1.8 GB for a daily 3-D variable), every rank regrids its own band
+    of TARGET latitudes (``split_rows``; the tables are those of the whole grid, the pole-row zonal means are
+    computed on every rank) and, with ``smooth``, first smooths the annual cycle of the whole source field
+    itself (1 ms on one B200: replicating that work is cheaper than any exchange of its result).  Returns
+    ``(band, (r0, r1), whole)``: this rank's rows [.., r1 - r0, nx] as a CUDA tensor, its row range, and -- with
+    ``gather`` -- the whole regridded field on rank ``src`` (None elsewhere), collected with one NCCL gather
+    of the bands.  ``data``: array / tensor holding the field on ``src``; on the other ranks anything of the same
+    shape (the broadcast overwrites it).  ``device`` / ``regrid_fn`` exist for the CPU (gloo) test of the
+    exchange logic; the product path is CUDA + ``functions.regrid_arrays``.
+    """
+    import torch
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    if regrid_fn is None:
+        from . import functions as F
+        regrid_fn = F.regrid_arrays
+    d = torch.as_tensor(data).to(dev, torch.float32).contiguous() if not isinstance(data, torch.Tensor) \
+        else data.to(dev, torch.float32).contiguous()
+    dist.broadcast(d, src=src, group=group)
+    if smooth:
+        from . import functions as F
+        d = F.smooth_annual_cycle(d)
+        if not isinstance(d, torch.Tensor):
+            d = torch.as_tensor(d, device=dev)
+    ny_t = len(targ_lat)
+    bounds = split_rows(ny_t, world)
+    r0, r1 = bounds[rank]
+    band = regrid_fn(d, lat_gcm, lon_gcm, targ_lat, targ_lon, rows=(r0, r1))
+    whole = None
+    if gather:
+        lead, nx_t = tuple(band.shape[:-2]), band.shape[-1]
+        # bands differ in their number of rows (721 = 7 x 90 + 91): gather equal-sized, row-major-in-band pieces
+        hmax = max(b - a for a, b in bounds)
+        piece = torch.zeros((hmax,) + lead + (nx_t,), device=dev, dtype=torch.float32)
+        piece[:r1 - r0] = band.movedim(-2, 0)
+        pieces = [torch.empty_like(piece) for _ in range(world)] if rank == src else None
+        dist.gather(piece, pieces, dst=src, group=group)
+        if rank == src:
+            whole = torch.empty(lead + (ny_t, nx_t), device=dev, dtype=torch.float32)
+            for (a, b), pc in zip(bounds, pieces):
+                whole[..., a:b, :] = pc[:b - a].movedim(0, -2)
+    return band, (r0, r1), whole
+
+
 def _parse_cpulist(text):
     cpus = set()
     for part in text.strip().split(","):

@@ -204,3 +204,56 @@ def test_byteswap32():
         N.check(N.lib.pgw_byteswap32(C.c_void_p(d.data_ptr()), n, C.c_void_p(torch.cuda.current_stream().cuda_stream)),
                 "pgw_byteswap32")
         np.testing.assert_array_equal(d.cpu().numpy(), x)
+
+
+def _regrid_with(path, F, *args, **kw):
+    import os
+    old = os.environ.get("PGW_REGRID_PATH")
+    if path:
+        os.environ["PGW_REGRID_PATH"] = path
+    try:
+        return F.regrid_arrays(*args, **kw)
+    finally:
+        if old is None:
+            os.environ.pop("PGW_REGRID_PATH", None)
+        else:
+            os.environ["PGW_REGRID_PATH"] = old
+
+
+@pytest.mark.parametrize("case", ["era_quarter", "flipped_irregular", "odd_nx", "many_source_rows"])
+def test_regrid_walk_kernel_bit_identical_and_banded(F, case):
+    """The walking kernel (source rows staged per chunk of target rows, three-column pattern) against the older
+    row and generic kernels -- same expressions, bit-identical -- and against the oracle; target-latitude bands
+     concatenate to the whole field bit for bit, for band edges that cut chunks and row pairs."""
+    rng = np.random.default_rng(31)
+    if case == "era_quarter":               # 1 degree -> 0.25 degree incl. both poles: the regular 4:1 pattern
+        lat, lon = np.linspace(-89.5, 89.5, 180), 0.5 + np.arange(360)
+        tlat, tlon = np.linspace(-90, 90, 721), 0.25 * np.arange(1440)
+        lead = (3,)
+    elif case == "flipped_irregular":       # north-to-south source, irregular longitudes: no three-column pattern
+        lat = np.linspace(80, -80, 41)
+        lon = np.sort(rng.uniform(0, 360, 97))
+        tlat, tlon = np.linspace(-75, 75, 61), np.linspace(lon[0] + 0.1, lon[-1] - 0.1, 200)
+        lead = (2, 3)
+    elif case == "odd_nx":                  # target width not a multiple of 4: scalar stores
+        lat, lon = np.linspace(-60, 60, 25), np.linspace(0, 100, 41)
+        tlat, tlon = np.linspace(-50, 50, 33), np.linspace(5, 95, 123)
+        lead = (4,)
+    else:                                   # finer source than target: a chunk spans more source rows than are staged
+        lat, lon = np.linspace(-80, 80, 321), np.linspace(0, 357, 120)
+        tlat, tlon = np.linspace(-70, 70, 29), np.linspace(1, 350, 64)
+        lead = (2,)
+    data = rng.normal(size=lead + (len(lat), len(lon))).astype(np.float32)
+    walk = _regrid_with(None, F, data, lat, lon, tlat, tlon)
+    rows = _regrid_with("rows", F, data, lat, lon, tlat, tlon)
+    gen = _regrid_with("generic", F, data, lat, lon, tlat, tlon)
+    np.testing.assert_array_equal(walk, gen)
+    np.testing.assert_array_equal(rows, gen)
+    ref = O.regrid_lat_lon(data, lat, lon, tlat, tlon)
+    np.testing.assert_allclose(walk, ref, rtol=0, atol=5e-7)
+    ny_t = len(tlat)
+    for bounds in ([0, 7, 8, 21, ny_t], [0, ny_t // 3, ny_t - 1, ny_t]):
+        parts = [F.regrid_arrays(data, lat, lon, tlat, tlon, rows=(a, b)) for a, b in zip(bounds[:-1], bounds[1:])]
+        np.testing.assert_array_equal(np.concatenate(parts, axis=-2), walk)
+    with pytest.raises(ValueError):
+        F.regrid_arrays(data, lat, lon, tlat, tlon, rows=(5, ny_t + 1))

@@ -80,3 +80,42 @@ def test_latband_and_broadcast_world2(tmp_path):
     np.testing.assert_allclose(ps, ref["PS"], rtol=0, atol=1e-9)      # bands reproduce the global field
     # a purely local rule would have stopped at least one band earlier or later than the global one
     assert max(n[0][1], n[1][1]) == ref["n_iter"]
+
+
+def _regrid_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import pgw_oracle as O
+    from pgw4era5_b200 import parallel as P
+    lat_s, lon_s = np.linspace(-87.5, 87.5, 36), 2.5 + 5.0 * np.arange(72)
+    lat_t, lon_t = np.linspace(-90, 90, 37), np.arange(0, 360, 2.5)
+    rng = np.random.default_rng(7)
+    field = rng.normal(size=(3, 2, 36, 72)).astype(np.float32)
+    data = torch.from_numpy(field) if rank == 0 else torch.full(field.shape, float(rank))   # garbage off rank 0
+
+    def oracle_band(d, la, lo, tla, tlo, rows):       # stands in for the CUDA operator on this GPU-less box
+        full = O.regrid_lat_lon(d.numpy().astype(np.float64), la, lo, tla, tlo)
+        return torch.from_numpy(full[..., rows[0]:rows[1], :].astype(np.float32))
+    band, (r0, r1), whole = P.regrid_banded(data, lat_s, lon_s, lat_t, lon_t, src=0, device="cpu",
+                                            regrid_fn=oracle_band)
+    assert (r0, r1) == P.split_rows(37, world)[rank] and band.shape == (3, 2, r1 - r0, 144)
+    if rank == 0:
+        np.save(os.path.join(out_dir, "whole.npy"), whole.numpy())
+        np.save(os.path.join(out_dir, "src.npy"), field)
+    else:
+        assert whole is None
+    dist.destroy_process_group()
+
+
+def test_regrid_banded_world3(tmp_path):
+    """SURVEY 8e row 3 on CPU (gloo, world 3: uneven bands 12 + 12 + 13): broadcast of the source field,
+    target-latitude bands, gather -- equals the oracle's regridding of the whole field."""
+    from oracle import pgw_oracle as O
+    world = 3
+    mp.spawn(_regrid_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    whole = np.load(str(tmp_path / "whole.npy"))
+    src = np.load(str(tmp_path / "src.npy"))
+    lat_s, lon_s = np.linspace(-87.5, 87.5, 36), 2.5 + 5.0 * np.arange(72)
+    lat_t, lon_t = np.linspace(-90, 90, 37), np.arange(0, 360, 2.5)
+    ref = O.regrid_lat_lon(src.astype(np.float64), lat_s, lon_s, lat_t, lon_t).astype(np.float32)
+    np.testing.assert_array_equal(whole, ref)
