@@ -168,32 +168,152 @@ regrid_rows_kernel(const float *__restrict__ src, float *__restrict__ dst, const
 // Walking variant (the production path for ERA5-sized targets): a CTA takes CHUNKS of kRegridChunk consecutive
 // target rows of one field.  (1) The few source rows the chunk needs (its rows j0..j1 span ~ chunk/4 + 2 rows of
 // a 1 degree source) are fetched ONCE with coalesced loads -- into registers while the previous chunk is being
-// computed, then parked in shared memory -- instead of four scattered gathers per thread and row pair; pole
-// rows (-1 / -2) read the zonal mean.  (2) Per pair of target rows the two bracketing source rows are blended
+// computed, then parked in shared memory next to two rows holding the pole means (the reference's synthetic
+// pole rows, functions.py:833-842) -- instead of four scattered gathers per thread and row pair.  A small table
+// per chunk turns (j0, j1, wy) of each target row into shared-memory offsets, so the latitude pass has no index
+// arithmetic and no pole-row branches.  (2) Per pair of target rows the two bracketing source rows are blended
 // in latitude once per source column into shared memory (functions.py:859, float64), (3) every thread produces
-// VEC adjacent target longitudes of both rows (:892) and writes one 16-byte streaming store per row.  The
-// VEC targets of a thread touch at most three distinct source columns when source and target grids are
-// regular, so three shared-memory loads serve all of them (checked once per launch, else 2 VEC loads).
+// VEC adjacent target longitudes of both rows (:892) and writes one 16-byte streaming store per row.  On regular
+// grids the VEC targets of every thread bracket (u0,u1) for the first N1 and (u1,u2) for the rest: three
+// shared-memory loads serve all of them and N1 is a template constant (checked once per launch; N1 = 0: the
+// general 2 VEC loads).  The older kernels spent 35 % of their instructions on addresses and ran out of issue
+// slots at 0.54 of the HBM peak; this one needs about a third of the instructions per point.
 // Same expressions as regrid_kernel, hence bit-identical.  `jt_begin, jt_end`: the band of target rows this
 // launch produces (dst holds only those rows): several GPUs split one variable by target latitude.
 constexpr int kRegridChunk = 8;        // target rows per chunk (even)
 constexpr int kRegridSrcRows = 6;      // source rows a chunk may span on the staged path
+struct __align__(16) RegridRow { int off_a, off_b; double w; };   // shared-memory offsets of the two source rows
 
+template <int VEC, int N1>
+__device__ __forceinline__ void regrid_walk_body(const float *__restrict__ src, float *__restrict__ dst,
+                                                 const float *__restrict__ polemean, int nfield, int ny_s, int nx_s,
+                                                 int nx_t, int jt_begin, int jt_end, const int *__restrict__ j0,
+                                                 const int *__restrict__ j1, const double *__restrict__ wy,
+                                                 const int (&ia)[VEC], const int (&ib)[VEC], const double (&w)[VEC],
+                                                 unsigned char *smem_raw) {
+    const int nrow = jt_end - jt_begin, nchunk = (nrow + kRegridChunk - 1) / kRegridChunk;
+    constexpr int SR = kRegridSrcRows;
+    double2 *const s_row = reinterpret_cast<double2 *>(smem_raw);                       // [2][nx_s]
+    RegridRow *const s_tab = reinterpret_cast<RegridRow *>(s_row + 2 * nx_s);           // [2][kRegridChunk]
+    float *const s_src = reinterpret_cast<float *>(s_tab + 2 * kRegridChunk);           // [2][SR + 2][nx_s]
+    const int2 *const s_chunk = reinterpret_cast<const int2 *>(s_src + 2 * (SR + 2) * nx_s);   // [nchunk]
+    const int tid = threadIdx.x;
+    const bool owner = tid < nx_t / VEC, col = tid < nx_s;
+    const int u0 = ia[0], u1 = ib[0], u2 = ib[VEC - 1];
+
+    const int nitem = nfield * nchunk;
+    float reg[SR], pm0 = 0.f, pm1 = 0.f;
+    auto prefetch = [&](int item) {
+        if (item >= nitem || !col) return;
+        const int f = item / nchunk, c = item - f * nchunk;
+        const int2 ch = s_chunk[c];
+        pm0 = __ldg(polemean + 2 * f); pm1 = __ldg(polemean + 2 * f + 1);
+        if (ch.y > SR) return;
+        const float *base = src + ((size_t)f * ny_s + ch.x) * (size_t)nx_s + tid;
+#pragma unroll
+        for (int r = 0; r < SR; ++r)
+            if (r < ch.y) reg[r] = __ldg(base + (size_t)r * nx_s);
+    };
+    int item = blockIdx.x, buf = 0, pb = 0;
+    prefetch(item);
+    for (; item < nitem; item += gridDim.x, buf ^= 1) {
+        const int f = item / nchunk, c = item - f * nchunk;
+        const int2 ch = s_chunk[c];
+        const bool staged = ch.y <= SR;
+        float *const ssrc = s_src + buf * (SR + 2) * nx_s;
+        const int r_begin = c * kRegridChunk, r_end = min(r_begin + kRegridChunk, nrow);
+        if (col) {
+            if (staged) {
+#pragma unroll
+                for (int r = 0; r < SR; ++r)
+                    if (r < ch.y) ssrc[r * nx_s + tid] = reg[r];
+            }
+            ssrc[SR * nx_s + tid] = pm0;                 // the two pole rows
+            ssrc[(SR + 1) * nx_s + tid] = pm1;
+        }
+        if (tid < kRegridChunk) {
+            const int jt = jt_begin + min(r_begin + tid, r_end - 1);
+            const int a = j0[jt], b = j1[jt];
+            // staged: offsets into ssrc; not staged (a chunk spanning many source rows): offsets into the field,
+            // negative = pole row
+            auto off = [&](int j) { return j == -1 ? SR * nx_s : (j == -2 ? (SR + 1) * nx_s : (j - ch.x) * nx_s); };
+            RegridRow t;
+            t.off_a = staged ? off(a) : (a < 0 ? a : a * nx_s);
+            t.off_b = staged ? off(b) : (b < 0 ? b : b * nx_s);
+            t.w = wy[jt];
+            s_tab[buf * kRegridChunk + tid] = t;
+        }
+        prefetch(item + gridDim.x);                 // in flight while this chunk is computed
+        const float *const fld = src + (size_t)f * ny_s * (size_t)nx_s;
+        float *o0 = dst + ((size_t)f * nrow + r_begin) * (size_t)nx_t + tid * VEC;
+        __syncthreads();                            // parked rows and the row table are visible
+        const RegridRow *tab = s_tab + buf * kRegridChunk;
+        for (int r = r_begin; r < r_end; r += 2, pb ^= 1, tab += 2, o0 += 2 * (size_t)nx_t) {
+            const bool two = r + 1 < r_end;
+            double2 *const row = s_row + pb * nx_s;
+            if (col) {
+                const RegridRow ta = tab[0], tb = tab[1];
+                double a0, a1, c0, c1;
+                if (staged) {
+                    a0 = (double)ssrc[ta.off_a + tid]; a1 = (double)ssrc[ta.off_b + tid];
+                    c0 = (double)ssrc[tb.off_a + tid]; c1 = (double)ssrc[tb.off_b + tid];
+                } else {
+                    auto at = [&](int o) { return (double)(o == -1 ? pm0 : (o == -2 ? pm1 : __ldg(fld + o + tid))); };
+                    a0 = at(ta.off_a); a1 = at(ta.off_b); c0 = at(tb.off_a); c1 = at(tb.off_b);
+                }
+                row[tid] = make_double2((a1 - a0) * ta.w + a0, (c1 - c0) * tb.w + c0);
+            }
+            __syncthreads();
+            if (owner) {
+                float r0[VEC], r1[VEC];
+                if (N1 > 0) {
+                    const double2 q0 = row[u0], q1 = row[u1], q2 = row[u2];
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) {
+                        const double2 a = v < N1 ? q0 : q1, b = v < N1 ? q1 : q2;
+                        r0[v] = (float)((b.x - a.x) * w[v] + a.x);
+                        r1[v] = (float)((b.y - a.y) * w[v] + a.y);
+                    }
+                } else {
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) {
+                        const double2 a = row[ia[v]], b = row[ib[v]];
+                        r0[v] = (float)((b.x - a.x) * w[v] + a.x);
+                        r1[v] = (float)((b.y - a.y) * w[v] + a.y);
+                    }
+                }
+                float *o1 = o0 + nx_t;
+                if (VEC == 4) {
+                    __stcs(reinterpret_cast<float4 *>(o0), make_float4(r0[0], r0[1], r0[2], r0[3]));
+                    if (two) __stcs(reinterpret_cast<float4 *>(o1), make_float4(r1[0], r1[1], r1[2], r1[3]));
+                } else {
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) {
+                        __stcs(o0 + v, r0[v]);
+                        if (two) __stcs(o1 + v, r1[v]);
+                    }
+                }
+            }
+        }
+    }
+}
+
+#ifndef PGW_REGRID_MINB
+#define PGW_REGRID_MINB 3
+#endif
 template <int VEC>
-__global__ void __launch_bounds__(384, 3)
+__global__ void __launch_bounds__(384, PGW_REGRID_MINB)
 regrid_walk_kernel(const float *__restrict__ src, float *__restrict__ dst, const float *__restrict__ polemean,
                    int nfield, int ny_s, int nx_s, int nx_t, int jt_begin, int jt_end,
                    const int *__restrict__ j0, const int *__restrict__ j1, const double *__restrict__ wy,
                    const int *__restrict__ i0, const int *__restrict__ i1, const double *__restrict__ wx) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int nrow = jt_end - jt_begin, nchunk = (nrow + kRegridChunk - 1) / kRegridChunk;
-    double2 *const s_row = reinterpret_cast<double2 *>(smem_raw);                       // [2][nx_s]
-    float *const s_src = reinterpret_cast<float *>(s_row + 2 * nx_s);                     // [2][kRegridSrcRows][nx_s]
-    int2 *const s_chunk = reinterpret_cast<int2 *>(s_src + 2 * kRegridSrcRows * nx_s);    // [nchunk] (jmin, span)
+    int2 *const s_chunk = reinterpret_cast<int2 *>(smem_raw + sizeof(double2) * 2 * nx_s +
+                                                   sizeof(RegridRow) * 2 * kRegridChunk +
+                                                   sizeof(float) * 2 * (kRegridSrcRows + 2) * nx_s);
     const int tid = threadIdx.x;
-    const int nxv = nx_t / VEC;
-    const bool owner = tid < nxv;
-
+    const bool owner = tid < nx_t / VEC;
     // ---- per launch: span of source rows of every chunk; longitude brackets of this thread
     for (int c = tid; c < nchunk; c += blockDim.x) {
         int lo = INT_MAX, hi = -1;
@@ -213,7 +333,7 @@ regrid_walk_kernel(const float *__restrict__ src, float *__restrict__ dst, const
         const int it = owner ? tid * VEC + v : 0;
         ia[v] = i0[it]; ib[v] = i1[it]; w[v] = wx[it];
     }
-    // three-column pattern: the first n1 targets bracket (u0, u1), the rest (u1, u2)
+    // three-column pattern: the first n1 targets bracket (u0, u1), the rest (u1, u2); n1 the same for all threads
     const int u0 = ia[0], u1 = ib[0], u2 = ib[VEC - 1];
     int n1 = 0;
     bool pat = true;
@@ -223,92 +343,31 @@ regrid_walk_kernel(const float *__restrict__ src, float *__restrict__ dst, const
         if (first && n1 == v) n1 = v + 1;
         else if (!second) pat = false;
     }
-    const bool three = __syncthreads_and(pat || !owner) != 0;       // also publishes s_chunk
-
-    const int nitem = nfield * nchunk;
-    float reg[kRegridSrcRows];
-    auto prefetch = [&](int item) {
-        if (item >= nitem || tid >= nx_s) return;
-        const int f = item / nchunk, c = item - f * nchunk;
-        const int2 ch = s_chunk[c];
-        if (ch.y > kRegridSrcRows) return;
-        const float *base = src + ((size_t)f * ny_s + ch.x) * (size_t)nx_s + tid;
-#pragma unroll
-        for (int r = 0; r < kRegridSrcRows; ++r)
-            if (r < ch.y) reg[r] = __ldg(base + (size_t)r * nx_s);
-    };
-    int item = blockIdx.x, buf = 0, pb = 0;
-    prefetch(item);
-    for (; item < nitem; item += gridDim.x, buf ^= 1) {
-        const int f = item / nchunk, c = item - f * nchunk;
-        const int2 ch = s_chunk[c];
-        const bool staged = ch.y <= kRegridSrcRows;
-        float *const ssrc = s_src + buf * kRegridSrcRows * nx_s;
-        if (staged && tid < nx_s) {
-#pragma unroll
-            for (int r = 0; r < kRegridSrcRows; ++r)
-                if (r < ch.y) ssrc[r * nx_s + tid] = reg[r];
-        }
-        prefetch(item + gridDim.x);                 // in flight while this chunk is computed
-        const float pm0 = __ldg(polemean + 2 * f), pm1 = __ldg(polemean + 2 * f + 1);
-        const float *const fld = src + (size_t)f * ny_s * (size_t)nx_s;
-        const int r_begin = c * kRegridChunk, r_end = min(r_begin + kRegridChunk, nrow);
-        // the parked rows become visible at the first barrier below
-        for (int r = r_begin; r < r_end; r += 2, pb ^= 1) {
-            const int jt0 = jt_begin + r, jt1 = min(jt0 + 1, jt_end - 1);
-            const bool two = r + 1 < r_end;
-            if (r == r_begin) __syncthreads();
-            double2 *const row = s_row + pb * nx_s;
-            if (tid < nx_s) {
-                auto at = [&](int j) -> double {
-                    if (j == -1) return (double)pm0;
-                    if (j == -2) return (double)pm1;
-                    return staged ? (double)ssrc[(j - ch.x) * nx_s + tid] : (double)__ldg(fld + (size_t)j * nx_s + tid);
-                };
-                const double a0 = at(j0[jt0]), a1 = at(j1[jt0]), c0 = at(j0[jt1]), c1 = at(j1[jt1]);
-                row[tid] = make_double2((a1 - a0) * wy[jt0] + a0, (c1 - c0) * wy[jt1] + c0);
-            }
-            __syncthreads();
-            if (owner) {
-                float r0[VEC], r1[VEC];
-                if (three) {
-                    const double2 q0 = row[u0], q1 = row[u1], q2 = row[u2];
-#pragma unroll
-                    for (int v = 0; v < VEC; ++v) {
-                        const bool fs = v < n1;
-                        const double ax = fs ? q0.x : q1.x, ay = fs ? q0.y : q1.y;
-                        const double bx = fs ? q1.x : q2.x, by = fs ? q1.y : q2.y;
-                        r0[v] = (float)((bx - ax) * w[v] + ax);
-                        r1[v] = (float)((by - ay) * w[v] + ay);
-                    }
-                } else {
-#pragma unroll
-                    for (int v = 0; v < VEC; ++v) {
-                        const double2 a = row[ia[v]], b = row[ib[v]];
-                        r0[v] = (float)((b.x - a.x) * w[v] + a.x);
-                        r1[v] = (float)((b.y - a.y) * w[v] + a.y);
-                    }
-                }
-                float *o0 = dst + ((size_t)f * nrow + r) * (size_t)nx_t + tid * VEC;
-                float *o1 = o0 + nx_t;
-                if (VEC == 4) {
-                    __stcs(reinterpret_cast<float4 *>(o0), make_float4(r0[0], r0[1], r0[2], r0[3]));
-                    if (two) __stcs(reinterpret_cast<float4 *>(o1), make_float4(r1[0], r1[1], r1[2], r1[3]));
-                } else {
-#pragma unroll
-                    for (int v = 0; v < VEC; ++v) {
-                        __stcs(o0 + v, r0[v]);
-                        if (two) __stcs(o1 + v, r1[v]);
-                    }
-                }
-            }
+    __shared__ int s_n1;
+    if (tid == 0) s_n1 = n1;
+    __syncthreads();                                // also publishes s_chunk
+    const int n1_all = s_n1;
+    const bool uniform = __syncthreads_and((pat && n1 == n1_all) || !owner) != 0;
+#define PGW_WALK(N) regrid_walk_body<VEC, N>(src, dst, polemean, nfield, ny_s, nx_s, nx_t, jt_begin, jt_end, j0, j1, wy, \
+                                             ia, ib, w, smem_raw)
+    if (uniform && VEC == 4) {
+        switch (n1_all) {
+            case 1: PGW_WALK(1); return;
+            case 2: PGW_WALK(2); return;
+            case 3: PGW_WALK(3); return;
+            case 4: PGW_WALK(4); return;
+            default: break;
         }
     }
+    PGW_WALK(0);
+#undef PGW_WALK
 }
 
 // harmonic_ac_analysis (functions.py:678-740): mean + harmonics 1..3 of an
 // nt-long series per grid point.  One thread per grid point, lanes = adjacent
 // points; cos/sin tables for the three harmonics are staged in shared memory.
+constexpr int kSmoothBatch = 8;
+
 __global__ void __launch_bounds__(128)
 smooth_kernel(const float *__restrict__ series, float *__restrict__ out, int nt, long long npoint) {
     extern __shared__ double tab[];                 // [nt][6]: cos1 sin1 cos2 sin2 cos3 sin3
@@ -324,8 +383,7 @@ smooth_kernel(const float *__restrict__ series, float *__restrict__ out, int nt,
          p += (long long)gridDim.x * blockDim.x) {
         double sum = 0.0, a1 = 0, b1 = 0, a2 = 0, b2 = 0, a3 = 0, b3 = 0;
         bool bad = false;
-        for (int t = 0; t < nt; ++t) {
-            const float xf = __ldcs(series + (long long)t * npoint + p);
+        auto acc = [&](float xf, int t) {
             bad |= isnan(xf);
             const double x = (double)xf;
             const double *tb = tab + t * 6;
@@ -333,11 +391,24 @@ smooth_kernel(const float *__restrict__ series, float *__restrict__ out, int nt,
             a1 = fma(x, tb[0], a1); b1 = fma(x, tb[1], b1);
             a2 = fma(x, tb[2], a2); b2 = fma(x, tb[3], b2);
             a3 = fma(x, tb[4], a3); b3 = fma(x, tb[5], b3);
+        };
+        // the series is read kSmoothBatch stamps at a time: that many independent loads in flight per thread (a
+        // load per iteration left the kernel waiting on DRAM latency: 59 % of its stall samples); same order of
+        // summation as before
+        const float *sp = series + p;
+        int t = 0;
+        for (; t + kSmoothBatch <= nt; t += kSmoothBatch) {
+            float xv[kSmoothBatch];
+#pragma unroll
+            for (int k = 0; k < kSmoothBatch; ++k) xv[k] = __ldcs(sp + (long long)(t + k) * npoint);
+#pragma unroll
+            for (int k = 0; k < kSmoothBatch; ++k) acc(xv[k], t + k);
         }
+        for (; t < nt; ++t) acc(__ldcs(sp + (long long)t * npoint), t);
         const double sc = 2. / (double)nt;
         const double mean = sum / (double)nt;
         a1 *= sc; b1 *= sc; a2 *= sc; b2 *= sc; a3 *= sc; b3 *= sc;
-        for (int t = 0; t < nt; ++t) {
+        for (t = 0; t < nt; ++t) {
             const double *tb = tab + t * 6;
             // sum(hcts[0:3]) + mean, functions.py:739 (python sum starts at 0)
             const double h = ((0.0 + (a1 * tb[0] + b1 * tb[1])) + (a2 * tb[2] + b2 * tb[3])) +
@@ -373,8 +444,8 @@ int pgw_regrid_bilinear_band_f32(const float *src, float *dst, const float *pole
     const bool walk_ok = (vec ? nx_t / 4 : nx_t) <= 384 && nx_s <= 384 && nfield * (long long)nchunk < (1LL << 31) &&
                          nchunk <= 4096 && !(force && (!strcmp(force, "rows") || !strcmp(force, "generic")));
     if (walk_ok) {
-        const size_t smem = sizeof(double2) * 2 * (size_t)nx_s + sizeof(float) * 2 * kRegridSrcRows * (size_t)nx_s +
-                            sizeof(int2) * (size_t)nchunk;
+        const size_t smem = sizeof(double2) * 2 * (size_t)nx_s + sizeof(RegridRow) * 2 * kRegridChunk +
+                            sizeof(float) * 2 * (kRegridSrcRows + 2) * (size_t)nx_s + sizeof(int2) * (size_t)nchunk;
         const long long nitem = nfield * (long long)nchunk;
         long long g = nitem < 148LL * 5 ? nitem : 148LL * 5;
         if (smem > 48 * 1024) {
@@ -438,11 +509,9 @@ int pgw_smooth_harmonic_f32(const float *series, float *out, int nt, long long n
     if (!series || !out || nt < 8 || npoint <= 0) return PGW_E_INVALID;     // i < floor(nt/2) for i=1..3
     const size_t smem = sizeof(double) * 6 * (size_t)nt;
     if (smem > 200 * 1024) return PGW_E_SMEM;
-    static thread_local size_t configured = 48 * 1024;
-    if (smem > configured) {
-        if (cudaFuncSetAttribute(smooth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-            return pgw_check_launch("cudaFuncSetAttribute(smooth_kernel)");
-        configured = smem;
+    if (smem > 48 * 1024) {
+        int rc;
+        if ((rc = pgw_ensure_smem((const void *)smooth_kernel, 14, smem, 0)) != PGW_OK) return rc;
     }
     long long g = (npoint + 127) / 128;
     const long long cap = 148LL * 8;
