@@ -401,6 +401,19 @@ def run_ours(a):
         sampler.mark_stop()
     ms = ev0.elapsed_time(ev1)
     kernel_ms = [e0.elapsed_time(e1) for e0, e1 in eng.kernel_events]
+    # time the GPU spent in the column kernel per launch: the union of the launches' intervals (with several
+    # streams the last wave of one launch runs next to the first wave of the following one; summing the
+    # individual durations would count that time twice)
+    iv = sorted((ev0.elapsed_time(e0), ev0.elapsed_time(e1)) for e0, e1 in eng.kernel_events)
+    busy, cur_a, cur_b = 0.0, None, None
+    for x, y in iv:
+        if cur_b is None or x > cur_b:
+            busy += (cur_b - cur_a) if cur_b is not None else 0.0
+            cur_a, cur_b = x, y
+        else:
+            cur_b = max(cur_b, y)
+    busy += (cur_b - cur_a) if cur_b is not None else 0.0
+    kernel_busy_ms = busy / max(1, len(iv))
     eng.kernel_events = None
     launches = eng.stats["launches"] - launches0
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
@@ -464,7 +477,7 @@ def run_ours(a):
     # ---- roofline of the dominant kernel (the fused column kernel)
     peak, peak_kind = measured_peak_gbs()
     abytes = algorithmic_bytes(ncol, 137, len(plev), len(era0["soil1"]))
-    k_ms = float(np.mean(kernel_ms)) if kernel_ms else None
+    k_ms = float(kernel_busy_ms) if kernel_ms else None
     achieved = abytes / (k_ms / 1000.0) / 1e9 if k_ms else None
     traffic, traffic_source = None, None
     try:
@@ -478,7 +491,11 @@ def run_ours(a):
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                 "traffic_source": traffic_source,
-                "kernel": kernel_name, "kernel_ms": k_ms, "algorithmic_bytes": abytes,
+                "kernel": kernel_name, "kernel_ms": k_ms,
+                "kernel_ms_how": "CUDA events around every launch (init + column kernel) inside the timed region; "
+                                 "union of the launches' intervals / launches (= the mean duration with one stream)",
+                "kernel_ms_mean_of_launch_durations": float(np.mean(kernel_ms)) if kernel_ms else None,
+                "algorithmic_bytes": abytes,
                 "peak_kind": peak_kind,
                 "frac_whole_step": abytes / (ms / a.steps / 1000.0) / 1e9 / peak}
 
@@ -541,7 +558,7 @@ def main():
     ap.add_argument("--e2e-slots", type=int, default=2, help="timesteps in flight in the host-buffer pipeline")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--inflight", type=int, default=4, help="timesteps queued before the host checks the oldest")
-    ap.add_argument("--streams", type=int, default=1, help="CUDA streams the timesteps alternate between")
+    ap.add_argument("--streams", type=int, default=2, help="CUDA streams the timesteps alternate between")
     ap.add_argument("--no-latband", action="store_true")
     ap.add_argument("--latband-snapshots", type=int, default=100)
     a = ap.parse_args()

@@ -6,6 +6,7 @@
 // smoothing reads and writes every series once.
 #include "pgw_common.cuh"
 
+#include <cuda_pipeline.h>
 #include <limits.h>
 #include <stdlib.h>
 #include <string.h>
@@ -180,9 +181,11 @@ regrid_rows_kernel(const float *__restrict__ src, float *__restrict__ dst, const
 // slots at 0.54 of the HBM peak; this one needs about a third of the instructions per point.
 // Same expressions as regrid_kernel, hence bit-identical.  `jt_begin, jt_end`: the band of target rows this
 // launch produces (dst holds only those rows): several GPUs split one variable by target latitude.
-constexpr int kRegridChunk = 8;        // target rows per chunk (even)
-constexpr int kRegridSrcRows = 6;      // source rows a chunk may span on the staged path
+constexpr int kRegridChunk = 16;       // target rows per chunk
+constexpr int kRegridGroup = 4;        // target rows per barrier (kRegridChunk is a multiple)
+constexpr int kRegridSrcRows = 6;      // source rows a chunk may span on the staged path (16 rows of a 4:1 regridding)
 struct __align__(16) RegridRow { int off_a, off_b; double w; };   // shared-memory offsets of the two source rows
+struct __align__(16) RegridQuad { double r[kRegridGroup]; };      // one source column, blended for a group of rows
 
 template <int VEC, int N1>
 __device__ __forceinline__ void regrid_walk_body(const float *__restrict__ src, float *__restrict__ dst,
@@ -192,42 +195,43 @@ __device__ __forceinline__ void regrid_walk_body(const float *__restrict__ src, 
                                                  const int (&ia)[VEC], const int (&ib)[VEC], const double (&w)[VEC],
                                                  unsigned char *smem_raw) {
     const int nrow = jt_end - jt_begin, nchunk = (nrow + kRegridChunk - 1) / kRegridChunk;
-    constexpr int SR = kRegridSrcRows;
-    double2 *const s_row = reinterpret_cast<double2 *>(smem_raw);                       // [2][nx_s]
-    RegridRow *const s_tab = reinterpret_cast<RegridRow *>(s_row + 2 * nx_s);           // [2][kRegridChunk]
-    float *const s_src = reinterpret_cast<float *>(s_tab + 2 * kRegridChunk);           // [2][SR + 2][nx_s]
-    const int2 *const s_chunk = reinterpret_cast<const int2 *>(s_src + 2 * (SR + 2) * nx_s);   // [nchunk]
+    constexpr int SR = kRegridSrcRows, G = kRegridGroup;
+    RegridQuad *const s_row = reinterpret_cast<RegridQuad *>(smem_raw);                 // [2][nx_s]
+    float *const s_src = reinterpret_cast<float *>(s_row + 2 * nx_s);                   // [2][SR + 2][nx_s]
+    RegridRow *const s_tab = reinterpret_cast<RegridRow *>(s_src + 2 * (SR + 2) * nx_s);   // [2][kRegridChunk]
+    const int2 *const s_chunk = reinterpret_cast<const int2 *>(s_tab + 2 * kRegridChunk);  // [nchunk] (jmin, span)
     const int tid = threadIdx.x;
     const bool owner = tid < nx_t / VEC, col = tid < nx_s;
     const int u0 = ia[0], u1 = ib[0], u2 = ib[VEC - 1];
 
-    const int nitem = nfield * nchunk;
-    float reg[SR], pm0 = 0.f, pm1 = 0.f;
-    auto prefetch = [&](int item) {
-        if (item >= nitem || !col) return;
-        const int f = item / nchunk, c = item - f * nchunk;
-        const int2 ch = s_chunk[c];
-        pm0 = __ldg(polemean + 2 * f); pm1 = __ldg(polemean + 2 * f + 1);
-        if (ch.y > SR) return;
-        const float *base = src + ((size_t)f * ny_s + ch.x) * (size_t)nx_s + tid;
+    // items (field, chunk) are walked with stride gridDim.x; (f, c) are advanced without a division
+    const int step_f = (int)(gridDim.x / (unsigned)nchunk), step_c = (int)(gridDim.x % (unsigned)nchunk);
+    int f = (int)(blockIdx.x / (unsigned)nchunk), c = (int)(blockIdx.x % (unsigned)nchunk);
+    // the source rows of the NEXT chunk travel global -> shared asynchronously (cp.async, no registers held)
+    // into the other half of s_src while this chunk is computed
+    float pm0 = 0.f, pm1 = 0.f;
+    auto prefetch = [&](int ff, int cc, int b) {
+        if (ff < nfield && col) {
+            const int2 ch = s_chunk[cc];
+            pm0 = __ldg(polemean + 2 * ff); pm1 = __ldg(polemean + 2 * ff + 1);
+            if (ch.y <= SR) {
+                const float *base = src + ((size_t)ff * ny_s + ch.x) * (size_t)nx_s + tid;
+                float *d = s_src + b * (SR + 2) * nx_s + tid;
 #pragma unroll
-        for (int r = 0; r < SR; ++r)
-            if (r < ch.y) reg[r] = __ldg(base + (size_t)r * nx_s);
+                for (int r = 0; r < SR; ++r)
+                    if (r < ch.y) __pipeline_memcpy_async(d + r * nx_s, base + (size_t)r * nx_s, 4);
+            }
+        }
+        __pipeline_commit();
     };
-    int item = blockIdx.x, buf = 0, pb = 0;
-    prefetch(item);
-    for (; item < nitem; item += gridDim.x, buf ^= 1) {
-        const int f = item / nchunk, c = item - f * nchunk;
+    int buf = 0, pb = 0;
+    prefetch(f, c, 0);
+    while (f < nfield) {
         const int2 ch = s_chunk[c];
         const bool staged = ch.y <= SR;
         float *const ssrc = s_src + buf * (SR + 2) * nx_s;
         const int r_begin = c * kRegridChunk, r_end = min(r_begin + kRegridChunk, nrow);
         if (col) {
-            if (staged) {
-#pragma unroll
-                for (int r = 0; r < SR; ++r)
-                    if (r < ch.y) ssrc[r * nx_s + tid] = reg[r];
-            }
             ssrc[SR * nx_s + tid] = pm0;                 // the two pole rows
             ssrc[(SR + 1) * nx_s + tid] = pm1;
         }
@@ -243,59 +247,97 @@ __device__ __forceinline__ void regrid_walk_body(const float *__restrict__ src, 
             t.w = wy[jt];
             s_tab[buf * kRegridChunk + tid] = t;
         }
-        prefetch(item + gridDim.x);                 // in flight while this chunk is computed
         const float *const fld = src + (size_t)f * ny_s * (size_t)nx_s;
         float *o0 = dst + ((size_t)f * nrow + r_begin) * (size_t)nx_t + tid * VEC;
+        const float pc0 = pm0, pc1 = pm1;
+        f += step_f; c += step_c;                   // next item
+        if (c >= nchunk) { c -= nchunk; ++f; }
+        __pipeline_wait_prior(0);                   // this chunk's rows have landed (own copies; barrier: everyone's)
         __syncthreads();                            // parked rows and the row table are visible
+        prefetch(f, c, buf ^ 1);                    // in flight while this chunk is computed; the last readers of
+                                                    // that half passed the barrier above
         const RegridRow *tab = s_tab + buf * kRegridChunk;
-        for (int r = r_begin; r < r_end; r += 2, pb ^= 1, tab += 2, o0 += 2 * (size_t)nx_t) {
-            const bool two = r + 1 < r_end;
-            double2 *const row = s_row + pb * nx_s;
+        for (int r = r_begin; r < r_end; r += G, pb ^= 1, tab += G, o0 += G * (size_t)nx_t) {
+            const int nvalid = min(G, r_end - r);
+            RegridQuad *const row = s_row + pb * nx_s;
             if (col) {
-                const RegridRow ta = tab[0], tb = tab[1];
-                double a0, a1, c0, c1;
-                if (staged) {
-                    a0 = (double)ssrc[ta.off_a + tid]; a1 = (double)ssrc[ta.off_b + tid];
-                    c0 = (double)ssrc[tb.off_a + tid]; c1 = (double)ssrc[tb.off_b + tid];
-                } else {
-                    auto at = [&](int o) { return (double)(o == -1 ? pm0 : (o == -2 ? pm1 : __ldg(fld + o + tid))); };
-                    a0 = at(ta.off_a); a1 = at(ta.off_b); c0 = at(tb.off_a); c1 = at(tb.off_b);
+                RegridQuad q;
+#pragma unroll
+                for (int k = 0; k < G; ++k) {
+                    const RegridRow t = tab[k];
+                    double a, b;
+                    if (staged) {
+                        a = (double)ssrc[t.off_a + tid]; b = (double)ssrc[t.off_b + tid];
+                    } else {
+                        auto at = [&](int o) { return (double)(o == -1 ? pc0 : (o == -2 ? pc1 : __ldg(fld + o + tid))); };
+                        a = at(t.off_a); b = at(t.off_b);
+                    }
+                    q.r[k] = (b - a) * t.w + a;     // latitude pass (functions.py:859)
                 }
-                row[tid] = make_double2((a1 - a0) * ta.w + a0, (c1 - c0) * tb.w + c0);
+                row[tid] = q;
             }
             __syncthreads();
             if (owner) {
-                float r0[VEC], r1[VEC];
-                if (N1 > 0) {
-                    const double2 q0 = row[u0], q1 = row[u1], q2 = row[u2];
+                // two rows at a time: the 16-byte halves of the quads (keeps the live registers of a thread low)
 #pragma unroll
-                    for (int v = 0; v < VEC; ++v) {
-                        const double2 a = v < N1 ? q0 : q1, b = v < N1 ? q1 : q2;
-                        r0[v] = (float)((b.x - a.x) * w[v] + a.x);
-                        r1[v] = (float)((b.y - a.y) * w[v] + a.y);
-                    }
-                } else {
+                for (int h = 0; h < G; h += 2) {
+                    if (h < nvalid) {
+                        float r0[VEC], r1[VEC];
+                        if (N1 > 0) {
+                            const double2 q0 = *reinterpret_cast<const double2 *>(&row[u0].r[h]);
+                            const double2 q1 = *reinterpret_cast<const double2 *>(&row[u1].r[h]);
+                            const double2 q2 = *reinterpret_cast<const double2 *>(&row[u2].r[h]);
 #pragma unroll
-                    for (int v = 0; v < VEC; ++v) {
-                        const double2 a = row[ia[v]], b = row[ib[v]];
-                        r0[v] = (float)((b.x - a.x) * w[v] + a.x);
-                        r1[v] = (float)((b.y - a.y) * w[v] + a.y);
-                    }
-                }
-                float *o1 = o0 + nx_t;
-                if (VEC == 4) {
-                    __stcs(reinterpret_cast<float4 *>(o0), make_float4(r0[0], r0[1], r0[2], r0[3]));
-                    if (two) __stcs(reinterpret_cast<float4 *>(o1), make_float4(r1[0], r1[1], r1[2], r1[3]));
-                } else {
+                            for (int v = 0; v < VEC; ++v) {
+                                const double2 a = v < N1 ? q0 : q1, b = v < N1 ? q1 : q2;
+                                r0[v] = (float)((b.x - a.x) * w[v] + a.x);      // longitude pass (:892)
+                                r1[v] = (float)((b.y - a.y) * w[v] + a.y);
+                            }
+                        } else {
 #pragma unroll
-                    for (int v = 0; v < VEC; ++v) {
-                        __stcs(o0 + v, r0[v]);
-                        if (two) __stcs(o1 + v, r1[v]);
+                            for (int v = 0; v < VEC; ++v) {
+                                const double2 a = *reinterpret_cast<const double2 *>(&row[ia[v]].r[h]);
+                                const double2 b = *reinterpret_cast<const double2 *>(&row[ib[v]].r[h]);
+                                r0[v] = (float)((b.x - a.x) * w[v] + a.x);
+                                r1[v] = (float)((b.y - a.y) * w[v] + a.y);
+                            }
+                        }
+                        float *oa = o0 + (size_t)h * nx_t, *ob = oa + nx_t;
+                        const bool two = h + 1 < nvalid;
+                        if (VEC == 4) {
+                            __stcs(reinterpret_cast<float4 *>(oa), make_float4(r0[0], r0[1], r0[2], r0[3]));
+                            if (two) __stcs(reinterpret_cast<float4 *>(ob), make_float4(r1[0], r1[1], r1[2], r1[3]));
+                        } else {
+#pragma unroll
+                            for (int v = 0; v < VEC; ++v) {
+                                __stcs(oa + v, r0[v]);
+                                if (two) __stcs(ob + v, r1[v]);
+                            }
+                        }
                     }
                 }
             }
         }
+        buf ^= 1;
     }
+}
+
+// the general path (any tables) out of line: its register needs must not shape the allocation of the hot bodies
+template <int VEC>
+__device__ __noinline__ void regrid_walk_general(const float *__restrict__ src, float *__restrict__ dst,
+                                                 const float *__restrict__ polemean, int nfield, int ny_s, int nx_s,
+                                                 int nx_t, int jt_begin, int jt_end, const int *__restrict__ j0,
+                                                 const int *__restrict__ j1, const double *__restrict__ wy,
+                                                 const int *__restrict__ i0, const int *__restrict__ i1,
+                                                 const double *__restrict__ wx, unsigned char *smem_raw) {
+    int ia[VEC], ib[VEC];
+    double w[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+        const int it = threadIdx.x < nx_t / VEC ? threadIdx.x * VEC + v : 0;
+        ia[v] = i0[it]; ib[v] = i1[it]; w[v] = wx[it];
+    }
+    regrid_walk_body<VEC, 0>(src, dst, polemean, nfield, ny_s, nx_s, nx_t, jt_begin, jt_end, j0, j1, wy, ia, ib, w, smem_raw);
 }
 
 #ifndef PGW_REGRID_MINB
@@ -309,9 +351,9 @@ regrid_walk_kernel(const float *__restrict__ src, float *__restrict__ dst, const
                    const int *__restrict__ i0, const int *__restrict__ i1, const double *__restrict__ wx) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int nrow = jt_end - jt_begin, nchunk = (nrow + kRegridChunk - 1) / kRegridChunk;
-    int2 *const s_chunk = reinterpret_cast<int2 *>(smem_raw + sizeof(double2) * 2 * nx_s +
-                                                   sizeof(RegridRow) * 2 * kRegridChunk +
-                                                   sizeof(float) * 2 * (kRegridSrcRows + 2) * nx_s);
+    int2 *const s_chunk = reinterpret_cast<int2 *>(smem_raw + sizeof(RegridQuad) * 2 * nx_s +
+                                                   sizeof(float) * 2 * (kRegridSrcRows + 2) * nx_s +
+                                                   sizeof(RegridRow) * 2 * kRegridChunk);
     const int tid = threadIdx.x;
     const bool owner = tid < nx_t / VEC;
     // ---- per launch: span of source rows of every chunk; longitude brackets of this thread
@@ -359,7 +401,7 @@ regrid_walk_kernel(const float *__restrict__ src, float *__restrict__ dst, const
             default: break;
         }
     }
-    PGW_WALK(0);
+    regrid_walk_general<VEC>(src, dst, polemean, nfield, ny_s, nx_s, nx_t, jt_begin, jt_end, j0, j1, wy, i0, i1, wx, smem_raw);
 #undef PGW_WALK
 }
 
@@ -444,7 +486,7 @@ int pgw_regrid_bilinear_band_f32(const float *src, float *dst, const float *pole
     const bool walk_ok = (vec ? nx_t / 4 : nx_t) <= 384 && nx_s <= 384 && nfield * (long long)nchunk < (1LL << 31) &&
                          nchunk <= 4096 && !(force && (!strcmp(force, "rows") || !strcmp(force, "generic")));
     if (walk_ok) {
-        const size_t smem = sizeof(double2) * 2 * (size_t)nx_s + sizeof(RegridRow) * 2 * kRegridChunk +
+        const size_t smem = sizeof(RegridQuad) * 2 * (size_t)nx_s + sizeof(RegridRow) * 2 * kRegridChunk +
                             sizeof(float) * 2 * (kRegridSrcRows + 2) * (size_t)nx_s + sizeof(int2) * (size_t)nchunk;
         const long long nitem = nfield * (long long)nchunk;
         long long g = nitem < 148LL * 5 ? nitem : 148LL * 5;

@@ -505,6 +505,9 @@ def regrid_tables(lat_gcm, lon_gcm, targ_lat, targ_lon):
                 i0=cols[ilo].astype(np.int32), i1=cols[ihi].astype(np.int32), wx=wx)
 
 
+_REGRID_TABLES = {}
+
+
 def regrid_arrays(data, lat_gcm, lon_gcm, targ_lat, targ_lon, rows=None):
     """
     regrid_lat_lon on arrays: data [..., nlat_gcm, nlon_gcm] -> [..., len(targ_lat),
@@ -514,17 +517,25 @@ def regrid_arrays(data, lat_gcm, lon_gcm, targ_lat, targ_lon, rows=None):
     rows of the whole field -- one variable split over several GPUs by target latitude
     (``parallel.regrid_banded``).
     """
-    tb = regrid_tables(lat_gcm, lon_gcm, targ_lat, targ_lon)
     d = _dev(data, torch.float32)
     ny_s, nx_s = d.shape[-2:]
     lead = tuple(d.shape[:-2])
     nfield = int(np.prod(lead)) if lead else 1
     dev = d.device
-    ti = lambda a: torch.as_tensor(np.ascontiguousarray(a), device=dev, dtype=torch.int32)
-    tf = lambda a: torch.as_tensor(np.ascontiguousarray(a), device=dev, dtype=torch.float64)
-    j0, j1, i0, i1 = ti(tb["j0"]), ti(tb["j1"]), ti(tb["i0"]), ti(tb["i1"])
-    wyd, wxd = tf(tb["wy"]), tf(tb["wx"])
-    ny_t, nx_t = len(tb["wy"]), len(tb["wx"])
+    # the tables depend on the four coordinate axes only: built once per grid pair and device (a daily 3-D
+    # variable, its HIST and SCEN-HIST files and every band of a multi-GPU split share them)
+    key = tuple(np.asarray(_raw(a), dtype=np.float64).tobytes() for a in (lat_gcm, lon_gcm, targ_lat, targ_lon)) + (str(dev),)
+    hit = _REGRID_TABLES.get(key)
+    if hit is None:
+        tb = regrid_tables(lat_gcm, lon_gcm, targ_lat, targ_lon)
+        ti = lambda a: torch.as_tensor(np.ascontiguousarray(a), device=dev, dtype=torch.int32)
+        tf = lambda a: torch.as_tensor(np.ascontiguousarray(a), device=dev, dtype=torch.float64)
+        hit = (ti(tb["j0"]), ti(tb["j1"]), ti(tb["i0"]), ti(tb["i1"]), tf(tb["wy"]), tf(tb["wx"]))
+        if len(_REGRID_TABLES) >= 8:
+            _REGRID_TABLES.clear()
+        _REGRID_TABLES[key] = hit
+    j0, j1, i0, i1, wyd, wxd = hit
+    ny_t, nx_t = wyd.numel(), wxd.numel()
     r0, r1 = (0, ny_t) if rows is None else (int(rows[0]), int(rows[1]))
     if not 0 <= r0 < r1 <= ny_t:
         raise ValueError("rows %r outside the %d target rows" % (rows, ny_t))

@@ -60,8 +60,11 @@ def main(rep):
     print("\nwarp instructions executed: %d" % tot_i)
     print("\nstall reasons (share of samples): " + ", ".join("%s %.1f%%" % (k, 100.0 * v / tot_s) for k, v in stall.most_common(8)))
     print("\nopcode mix: " + ", ".join("%s %.1f%%" % (k, 100.0 * v / tot_i) for k, v in ops.most_common(20)))
-    json.dump({"dram_bytes_per_launch": rd + wr, "dram_read": rd, "dram_write": wr, "source": os.path.basename(rep)},
-              open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "column_kernel_traffic.json"), "w"))
+    # bench.py reads the DRAM traffic of the COLUMN kernel from this file (roofline.traffic): only a capture of that
+    # kernel may update it
+    if "pgw_column" in m.get('Kernel Name', ('', ''))[0]:
+        json.dump({"dram_bytes_per_launch": rd + wr, "dram_read": rd, "dram_write": wr, "source": os.path.basename(rep)},
+                  open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "column_kernel_traffic.json"), "w"))
 
 
 if __name__ == "__main__":

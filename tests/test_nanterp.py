@@ -155,3 +155,41 @@ def test_all_nan_source_gives_all_nan():
     glat, glon, vals, tlat, tlon, land_fr, radius = _ocean_case(6, False)
     out = F.nan_ignoring_interp_arrays(land_fr, tlat, tlon, np.full_like(vals, np.nan), glat, glon, radius, 4.0)
     assert out.shape == (3, len(tlat), len(tlon)) and np.all(np.isnan(out))
+
+
+# ---------------------------------------------------------------------------------------------
+# against pyproj / VTK themselves, once somebody has run oracle/make_golden_nanterp.py where those packages exist
+# ---------------------------------------------------------------------------------------------
+def _pyproj_vtk_fixture():
+    import os
+    path = os.path.join(os.path.dirname(__file__), "golden", "reference_nanterp.npz")
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/reference_nanterp.npz not generated yet (needs pyproj + pyvista, absent here): "
+                    "run oracle/make_golden_nanterp.py; until then this operator is PARITY UNPINNED")
+    return np.load(path)
+
+
+def test_oracle_matches_pyproj_vtk_fixture():
+    """The oracle's restatement against what the UNMODIFIED reference returned with real pyproj and pyvista."""
+    G = _pyproj_vtk_fixture()
+    lon = G["gcm_lon2d"].reshape(-1).copy()
+    lon[lon > 180] -= 360
+    lat_m, lon_m = O.lonlat_to_meter(lon, G["gcm_lat2d"].reshape(-1))
+    np.testing.assert_allclose(np.abs(lat_m), G["geod_lat_m"], rtol=0, atol=1e-3)         # 1 mm
+    np.testing.assert_allclose(np.abs(lon_m), G["geod_lon_m"], rtol=0, atol=1e-3)
+    np.testing.assert_allclose(O.wgs84_half_turn_distance(G["gcm_lat2d"].reshape(-1)), G["geod_half_turn"], rtol=0, atol=1e-3)
+    out = O.nan_ignoring_interp(G["land_fr"], G["era5_lat"], G["era5_lon"], G["tos"], G["gcm_lat2d"], G["gcm_lon2d"],
+                                float(G["kernel_radius"]), float(G["sharpness"]))
+    assert np.array_equal(np.isnan(out), np.isnan(G["result"]))
+    np.testing.assert_allclose(out, G["result"], rtol=0, atol=1e-9, equal_nan=True)
+
+
+@pytest.mark.gpu
+def test_cuda_matches_pyproj_vtk_fixture():
+    from pgw4era5_b200 import functions as F
+    G = _pyproj_vtk_fixture()
+    out = F.nan_ignoring_interp_arrays(G["land_fr"], G["era5_lat"], G["era5_lon"], G["tos"], G["gcm_lat2d"],
+                                       G["gcm_lon2d"], float(G["kernel_radius"]), float(G["sharpness"]))
+    out = np.asarray(out.cpu() if hasattr(out, "cpu") else out)
+    assert np.array_equal(np.isnan(out), np.isnan(G["result"]))
+    np.testing.assert_allclose(out, G["result"], rtol=0, atol=1e-9, equal_nan=True)
