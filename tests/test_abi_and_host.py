@@ -226,3 +226,47 @@ def test_decode_time_calendars():
     # negative offsets
     got = ncio.decode_time(V(("time",), np.array([-1.0]), {"units": "days since 2001-01-01", "calendar": "360_day"}))
     assert got[0] == np.datetime64("2000-12-30")
+
+
+def test_error_bits_of_iterations_the_reference_never_ran_are_ignored(monkeypatch):
+    """The kernel runs k_spec iterations for every column, the reference stops after N.  PGW_ERR_PREF_BELOW_SFC /
+    PGW_ERR_PS_BOUND that first fired in an iteration >= N (status.first_k) did not happen in the reference:
+    no error, no rerun.  Host logic of PGWEngine._complete on a hand-made status block (no GPU needed)."""
+    import types
+    from pgw4era5_b200 import _native as N
+    from pgw4era5_b200 import engine as E
+
+    def run(err, first_k, n_iter, converged=1, k_spec=8):
+        st = N.TimestepStatus()
+        st.err = err
+        st.first_k[0], st.first_k[1] = first_k
+        st.result.n_iter, st.result.converged, st.result.rewritten = n_iter, converged, 0
+        st.stats[0], st.stats[1] = 500.0, 100.0
+        eng = object.__new__(E.PGWEngine)
+        eng.deltas = types.SimpleNamespace(plev=np.array([100000.0, 100.0]))
+        eng.stats = dict(timesteps=0, rewrites=0, reruns=0, launches=0)
+        eng._n_hist, eng.k_pred, eng.ps_bound = [], 8, 110000.0
+        eng.submit = lambda *a, **k: (_ for _ in ()).throw(AssertionError("rerun"))
+        import contextlib
+        p = types.SimpleNamespace(snapshot=lambda: st, out={}, ctx=dict(
+            ignore_top=True, k_spec=k_spec, k_max=19, file_name="f", stream=None, era=None, when=None, slot=0,
+            direct=False))
+        E.torch.cuda.stream = lambda s: contextlib.nullcontext()
+        return E.PGWEngine._complete(eng, p)
+
+    big = N.INT32_MAX
+    from pgw4era5_b200 import settings
+    monkeypatch.setattr(settings, "i_debug", 0)
+    monkeypatch.setattr(E.torch.cuda, "stream", E.torch.cuda.stream)      # restored after the test
+    assert run(0, (big, big), 6)["n_iter"] == 6
+    # fired only in the speculative iterations 6, 7 (0-based) of k_spec = 8 while the reference stopped after 6
+    assert run(N.ERR_PREF_BELOW_SFC, (6, big), 6)["n_iter"] == 6
+    assert run(N.ERR_PS_BOUND, (big, 7), 6)["n_iter"] == 6
+    # fired in an iteration the reference did run
+    with pytest.raises(ValueError, match="below the surface"):
+        run(N.ERR_PREF_BELOW_SFC, (5, big), 6)
+    with pytest.raises(AssertionError, match="rerun"):
+        run(N.ERR_PS_BOUND, (big, 2), 6)
+    # not converged: every one of the k_spec iterations counts
+    with pytest.raises(ValueError, match="below the surface"):
+        run(N.ERR_PREF_BELOW_SFC, (7, big), 0, converged=0)
