@@ -168,7 +168,7 @@ regrid_rows_kernel(const float *__restrict__ src, float *__restrict__ dst, const
 
 // Walking variant (the production path for ERA5-sized targets): a CTA takes CHUNKS of kRegridChunk consecutive
 // target rows of one field.  (1) The few source rows the chunk needs (its rows j0..j1 span ~ chunk/4 + 2 rows of
-// a 1 degree source) are fetched ONCE with coalesced loads -- into registers while the previous chunk is being
+// a 1 degree source; chunks of 8 / 16 / 32 rows: 6.76 / 6.52 / 6.22 ms) are fetched ONCE with coalesced loads -- into registers while the previous chunk is being
 // computed, then parked in shared memory next to two rows holding the pole means (the reference's synthetic
 // pole rows, functions.py:833-842) -- instead of four scattered gathers per thread and row pair.  A small table
 // per chunk turns (j0, j1, wy) of each target row into shared-memory offsets, so the latitude pass has no index
@@ -181,9 +181,15 @@ regrid_rows_kernel(const float *__restrict__ src, float *__restrict__ dst, const
 // slots at 0.54 of the HBM peak; this one needs about a third of the instructions per point.
 // Same expressions as regrid_kernel, hence bit-identical.  `jt_begin, jt_end`: the band of target rows this
 // launch produces (dst holds only those rows): several GPUs split one variable by target latitude.
-constexpr int kRegridChunk = 16;       // target rows per chunk
+#ifndef PGW_REGRID_CHUNK
+#define PGW_REGRID_CHUNK 32
+#endif
+#ifndef PGW_REGRID_SR
+#define PGW_REGRID_SR 10
+#endif
+constexpr int kRegridChunk = PGW_REGRID_CHUNK;   // target rows per chunk
 constexpr int kRegridGroup = 4;        // target rows per barrier (kRegridChunk is a multiple)
-constexpr int kRegridSrcRows = 6;      // source rows a chunk may span on the staged path (16 rows of a 4:1 regridding)
+constexpr int kRegridSrcRows = PGW_REGRID_SR;      // source rows a chunk may span on the staged path (32 rows of a 4:1 regridding: 8 intervals + 2)
 struct __align__(16) RegridRow { int off_a, off_b; double w; };   // shared-memory offsets of the two source rows
 struct __align__(16) RegridQuad { double r[kRegridGroup]; };      // one source column, blended for a group of rows
 
@@ -408,9 +414,18 @@ regrid_walk_kernel(const float *__restrict__ src, float *__restrict__ dst, const
 // harmonic_ac_analysis (functions.py:678-740): mean + harmonics 1..3 of an
 // nt-long series per grid point.  One thread per grid point, lanes = adjacent
 // points; cos/sin tables for the three harmonics are staged in shared memory.
-constexpr int kSmoothBatch = 8;
+#ifndef PGW_SMOOTH_BATCH
+#define PGW_SMOOTH_BATCH 8
+#endif
+#ifndef PGW_SMOOTH_THREADS
+#define PGW_SMOOTH_THREADS 128
+#endif
+#ifndef PGW_SMOOTH_CAP
+#define PGW_SMOOTH_CAP 8
+#endif
+constexpr int kSmoothBatch = PGW_SMOOTH_BATCH, kSmoothThreads = PGW_SMOOTH_THREADS;
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(kSmoothThreads)
 smooth_kernel(const float *__restrict__ series, float *__restrict__ out, int nt, long long npoint) {
     extern __shared__ double tab[];                 // [nt][6]: cos1 sin1 cos2 sin2 cos3 sin3
     for (int t = threadIdx.x; t < nt; t += blockDim.x) {
@@ -555,10 +570,10 @@ int pgw_smooth_harmonic_f32(const float *series, float *out, int nt, long long n
         int rc;
         if ((rc = pgw_ensure_smem((const void *)smooth_kernel, 14, smem, 0)) != PGW_OK) return rc;
     }
-    long long g = (npoint + 127) / 128;
-    const long long cap = 148LL * 8;
+    long long g = (npoint + kSmoothThreads - 1) / kSmoothThreads;
+    const long long cap = 148LL * PGW_SMOOTH_CAP;
     if (g > cap) g = cap;
-    smooth_kernel<<<(unsigned)g, 128, smem, (cudaStream_t)stream>>>(series, out, nt, npoint);
+    smooth_kernel<<<(unsigned)g, kSmoothThreads, smem, (cudaStream_t)stream>>>(series, out, nt, npoint);
     return pgw_check_launch("smooth_kernel");
 }
 
