@@ -28,7 +28,7 @@ extern "C" {
 #endif
 
 #define PGW_B200_ABI_VERSION 6   /* 6: + pgw_timestep_status, pgw_timestep_run/_finish, PGW_FLAG_REF_DTYPES, first_k,
-                                       pgw_band_pack/_unpack, pgw_regrid_bilinear_band_f32 */
+                                       pgw_band_pack/_unpack, pgw_band_exchange, pgw_regrid_bilinear_band_f32 */
 
 /* host-side return codes */
 #define PGW_OK               0
@@ -43,6 +43,7 @@ extern "C" {
 #define PGW_ERR_PS_HIST_RANGE       (1u << 4)  /* functions.py:360-361,363 */
 #define PGW_ERR_PREF_BELOW_SFC      (1u << 5)  /* functions.py:162-165 */
 #define PGW_ERR_NO_PREF             (1u << 6)  /* step_03_apply_to_era.py:245-251 */
+#define PGW_ERR_BAND_TIMEOUT        (1u << 8)  /* pgw_band_exchange: a peer's status block did not arrive */
 #define PGW_ERR_PS_BOUND            (1u << 7)  /* ps left the range the column
                                                   stash was sized for: rerun
                                                   with a larger ps_bound */
@@ -310,6 +311,19 @@ int pgw_timestep_finish(const pgw_timestep_args *a, pgw_timestep_status *status_
 #define PGW_BAND_WORDS (PGW_MAX_ITER + 2 + 32 + 2)
 int pgw_band_pack(const pgw_timestep_status *status_dev, double *words_dev, void *stream);
 int pgw_band_unpack(const double *words_dev, pgw_timestep_status *status_dev, void *stream);
+/* The same exchange WITHOUT a collective library, as one kernel over peer memory (NVLink / NVSwitch): every rank owns
+ * an inbox of PGW_BAND_PARITIES x world x PGW_BAND_SLOT float64 in memory its peers can store to (CUDA IPC / VMM
+ * peer mappings, e.g. torch symmetric memory); inbox_ptrs_dev[r] is rank r's inbox as seen from this GPU.
+ * The kernel packs this band's status block, stores it into slot [seq % parities][rank] of EVERY inbox, publishes it
+ * with a system-scope release of the slot's flag word (= seq), waits until all `world` flags of its own inbox carry
+ * seq, merges the blocks (MAX) and unpacks the result into status_dev -- launched on the stream right behind the
+ * column kernel, it is the collective fused into the step: no host round trip, no second library, ~100 stores per
+ * peer.  seq must increase by one per snapshot, identically on all ranks, starting at 1 on a zeroed inbox.  A peer
+ * that does not deliver within timeout_s sets PGW_ERR_BAND_TIMEOUT (the kernel never spins for ever). */
+#define PGW_BAND_SLOT      (PGW_BAND_WORDS + 4)   /* words per slot: the block, the flag, padding */
+#define PGW_BAND_PARITIES  8
+int pgw_band_exchange(pgw_timestep_status *status_dev, double *const *inbox_ptrs_dev, int rank, int world,
+                      unsigned long long seq, double timeout_s, void *stream);
 
 /* ------------------------------------------------------------------------
  * The staged per-timestep path: pgw_for_era5() run stage by stage on float64

@@ -25,6 +25,9 @@ ERR_PS_HIST_RANGE = 1 << 4
 ERR_PREF_BELOW_SFC = 1 << 5
 ERR_NO_PREF = 1 << 6
 ERR_PS_BOUND = 1 << 7
+ERR_BAND_TIMEOUT = 1 << 8
+BAND_SLOT = 64 + 2 + 32 + 2 + 4
+BAND_PARITIES = 8
 FLAG_DIRECT = 1
 FLAG_REF_DTYPES = 2
 RUN_NO_FINALIZE = 1
@@ -113,6 +116,7 @@ def _load():
         "pgw_timestep_finish": (i, [C.POINTER(TimestepArgs), vp, vp, vp]),
         "pgw_band_pack": (i, [vp, vp, vp]),
         "pgw_band_unpack": (i, [vp, vp, vp]),
+        "pgw_band_exchange": (i, [vp, vp, i, i, C.c_ulonglong, d, vp]),
         "pgw_zonal_mean_f32": (i, [vp, vp, ll, i, i, vp]),
         "pgw_regrid_bilinear_f32": (i, [vp, vp, vp, ll, i, i, i, i, vp, vp, vp, vp, vp, vp, vp]),
         "pgw_regrid_bilinear_band_f32": (i, [vp, vp, vp, ll, i, i, i, i, i, i, vp, vp, vp, vp, vp, vp, vp]),

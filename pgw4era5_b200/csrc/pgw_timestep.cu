@@ -606,6 +606,80 @@ __global__ void pgw_band_unpack_kernel(const double *w, pgw_timestep_status *s) 
     } else if (i >= PGW_MAX_ITER + 34 && i < PGW_BAND_WORDS) s->first_k[i - PGW_MAX_ITER - 34] = (int32_t)(-w[i]);
 }
 
+// Latitude-band exchange fused into the step: pack, store into every peer's inbox over NVLink, release a flag,
+// wait for all peers' flags, merge (MAX), unpack.  One CTA of 128 threads; see pgw_band_exchange in the header.
+__device__ __forceinline__ void st_sys_f64(double *p, double v) {
+    asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ void st_release_sys_f64(double *p, double v) {
+    asm volatile("st.release.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ double ld_acquire_sys_f64(const double *p) {
+    double v;
+    asm volatile("ld.acquire.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ double ld_sys_f64(const double *p) {
+    double v;
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(128)
+pgw_band_exchange_kernel(pgw_timestep_status *s, double *const *inbox, int rank, int world, unsigned long long seq,
+                         long long timeout_ns) {
+    __shared__ double merged[PGW_BAND_WORDS];
+    __shared__ int timed_out;
+    const int i = threadIdx.x;
+    const size_t par = (size_t)(seq % PGW_BAND_PARITIES);
+    const double tag = (double)seq;
+    if (i == 0) timed_out = 0;
+    // ---- pack (same words as pgw_band_pack_kernel)
+    double w = 0.0;
+    if (i < PGW_MAX_ITER) w = __longlong_as_double((long long)s->maxerr[i]);
+    else if (i < PGW_MAX_ITER + 2) w = -(double)s->stats[i - PGW_MAX_ITER];
+    else if (i < PGW_MAX_ITER + 34) w = (double)((s->err >> (i - PGW_MAX_ITER - 2)) & 1u);
+    else if (i < PGW_BAND_WORDS) w = -(double)s->first_k[i - PGW_MAX_ITER - 34];
+    // ---- push this band's block into slot [par][rank] of every inbox (its own included)
+    const size_t slot = (par * (size_t)world + (size_t)rank) * PGW_BAND_SLOT;
+    if (i < PGW_BAND_WORDS)
+        for (int r = 0; r < world; ++r) st_sys_f64(inbox[r] + slot + i, w);
+    __threadfence_system();
+    __syncthreads();
+    if (i < world) st_release_sys_f64(inbox[i] + slot + PGW_BAND_WORDS, tag);     // thread i publishes to peer i
+    // ---- wait for the blocks of all bands in the own inbox
+    const double *mine = inbox[rank] + par * (size_t)world * PGW_BAND_SLOT;
+    if (i < world) {
+        long long t0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        while (ld_acquire_sys_f64(mine + (size_t)i * PGW_BAND_SLOT + PGW_BAND_WORDS) != tag) {
+            long long t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > timeout_ns) { timed_out = 1; break; }
+            __nanosleep(200);
+        }
+    }
+    __syncthreads();
+    if (timed_out) {
+        if (i == 0) atomicOr(&s->err, PGW_ERR_BAND_TIMEOUT);
+        return;
+    }
+    // ---- merge (element-wise MAX over the bands) and unpack
+    if (i < PGW_BAND_WORDS) {
+        double m = ld_sys_f64(mine + i);
+        for (int r = 1; r < world; ++r) m = fmax(m, ld_sys_f64(mine + (size_t)r * PGW_BAND_SLOT + i));
+        merged[i] = m;
+    }
+    __syncthreads();
+    if (i < PGW_MAX_ITER) s->maxerr[i] = (uint64_t)__double_as_longlong(merged[i]);
+    else if (i < PGW_MAX_ITER + 2) s->stats[i - PGW_MAX_ITER] = (float)(-merged[i]);
+    else if (i == PGW_MAX_ITER + 2) {
+        uint32_t e = 0;
+        for (int b = 0; b < 32; ++b) if (merged[PGW_MAX_ITER + 2 + b] != 0.0) e |= 1u << b;
+        s->err = e;
+    } else if (i >= PGW_MAX_ITER + 34 && i < PGW_BAND_WORDS) s->first_k[i - PGW_MAX_ITER - 34] = (int32_t)(-merged[i]);
+}
+
 }  // namespace pgw
 
 // ---------------------------------------------------------------------------
@@ -762,6 +836,16 @@ int pgw_band_pack(const pgw_timestep_status *status_dev, double *words_dev, void
     if (!status_dev || !words_dev) return PGW_E_INVALID;
     pgw::pgw_band_pack_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(status_dev, words_dev);
     return pgw_check_launch("pgw_band_pack");
+}
+
+int pgw_band_exchange(pgw_timestep_status *status_dev, double *const *inbox_ptrs_dev, int rank, int world,
+                      unsigned long long seq, double timeout_s, void *stream) {
+    if (!status_dev || !inbox_ptrs_dev || world < 1 || world > 128 || rank < 0 || rank >= world || seq == 0 ||
+        !(timeout_s > 0.0))
+        return PGW_E_INVALID;
+    pgw::pgw_band_exchange_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(status_dev, inbox_ptrs_dev, rank, world, seq,
+                                                                        (long long)(timeout_s * 1e9));
+    return pgw_check_launch("pgw_band_exchange");
 }
 
 int pgw_band_unpack(const double *words_dev, pgw_timestep_status *status_dev, void *stream) {

@@ -215,7 +215,8 @@ class PGWEngine:
     step_03_apply_to_era.py:68-85); soil1: soil depths [S].
     """
 
-    def __init__(self, ak, bk, deltas, soil1=(), akm=None, bkm=None, ps_bound=110000.0, group=None):
+    def __init__(self, ak, bk, deltas, soil1=(), akm=None, bkm=None, ps_bound=110000.0, group=None,
+                 band_exchange="auto"):
         if not torch.cuda.is_available():
             raise RuntimeError("PGWEngine needs a CUDA device (B200, sm_100a); there is no CPU path")
         self.deltas = deltas
@@ -238,12 +239,50 @@ class PGWEngine:
         self.soil_decay = np.exp(-soil1 / 2.8).astype(np.float64)     # step_03:140
         self.ps_bound = float(ps_bound)
         self.group = group
+        # latitude-band mode: how the bands agree on the iteration count.  "p2p": pgw_band_exchange, one kernel over
+        # peer memory behind the column kernel (inboxes in torch symmetric memory); "nccl": pack, all-reduce(MAX),
+        # unpack; "auto": p2p where the peer mapping can be set up, else nccl.
+        self.band_exchange = None
+        self._xseq = 0
+        if group is not None:
+            self.band_exchange = self._setup_band_exchange(band_exchange)
         self.k_pred = 8
         self._n_hist = []               # iteration counts of the last few timesteps
         self._ws = {}
         self._zg_level = {}
         self.stats = dict(timesteps=0, rewrites=0, reruns=0, launches=0)
         self.kernel_events = None       # set to [] to collect CUDA events around the column kernel
+
+    def _setup_band_exchange(self, mode):
+        import torch.distributed as dist
+        if mode not in ("auto", "p2p", "nccl"):
+            raise ValueError("band_exchange must be 'auto', 'p2p' or 'nccl'")
+        if mode == "nccl":
+            return "nccl"
+        world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        ok, err = 1, None
+        try:
+            import torch.distributed._symmetric_memory as symm
+            n = N.BAND_PARITIES * world * N.BAND_SLOT
+            box = symm.empty(n, dtype=torch.float64, device=self.device)
+            box.zero_()
+            hdl = symm.rendezvous(box, self.group)
+            ptrs = [int(p) for p in hdl.buffer_ptrs]
+            if len(ptrs) != world or not all(ptrs):
+                raise RuntimeError("symmetric memory returned no peer pointers")
+            self._inbox, self._inbox_hdl = box, hdl
+            self._inbox_ptrs = torch.tensor(ptrs, dtype=torch.int64, device=self.device)
+            self._xrank, self._xworld = rank, world
+        except Exception as e:           # no peer mapping on this platform: the NCCL form of the same exchange
+            ok, err = 0, e
+        flag = torch.tensor([ok], device=self.device, dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)       # all ranks take the same path
+        torch.cuda.synchronize()
+        if int(flag.item()) == 1:
+            return "p2p"
+        if mode == "p2p":
+            raise RuntimeError("peer-memory band exchange not available: %r" % (err,))
+        return "nccl"
 
     # ------------------------------------------------------------------ workspace
     def _workspace(self, ncol, max_iter, slot=0):
@@ -303,12 +342,18 @@ class PGWEngine:
             if self.group is not None:
                 # latitude-band mode: the stopping rule is global over all bands (step_03:189,308).  ONE
                 # collective merges the whole status block: max error per iteration, error bits, minima.
-                import torch.distributed as dist
-                w = ws["band_words"]
-                N.check(N.lib.pgw_band_pack(sdev, C.c_void_p(w.data_ptr()), st), "pgw_band_pack")
-                dist.all_reduce(w, op=dist.ReduceOp.MAX, group=self.group)
-                N.check(N.lib.pgw_band_unpack(C.c_void_p(w.data_ptr()), sdev, st), "pgw_band_unpack")
-                self.stats["launches"] += 2
+                if self.band_exchange == "p2p":
+                    self._xseq += 1
+                    N.check(N.lib.pgw_band_exchange(sdev, C.c_void_p(self._inbox_ptrs.data_ptr()), self._xrank,
+                                                    self._xworld, self._xseq, 20.0, st), "pgw_band_exchange")
+                    self.stats["launches"] += 1
+                else:
+                    import torch.distributed as dist
+                    w = ws["band_words"]
+                    N.check(N.lib.pgw_band_pack(sdev, C.c_void_p(w.data_ptr()), st), "pgw_band_pack")
+                    dist.all_reduce(w, op=dist.ReduceOp.MAX, group=self.group)
+                    N.check(N.lib.pgw_band_unpack(C.c_void_p(w.data_ptr()), sdev, st), "pgw_band_unpack")
+                    self.stats["launches"] += 2
             N.check(N.lib.pgw_timestep_finish(C.byref(a), sdev, shost, st), "pgw_timestep_finish")
         self.stats["launches"] += 4
         ws["event"].record()
@@ -426,6 +471,8 @@ class PGWEngine:
             err &= ~N.ERR_PREF_BELOW_SFC
         if (err & N.ERR_PS_BOUND) and st.first_k[1] >= n_ran:
             err &= ~N.ERR_PS_BOUND
+        if err & N.ERR_BAND_TIMEOUT:
+            raise RuntimeError("latitude-band exchange: the status block of a peer rank did not arrive")
         if err & N.ERR_PS_HIST_RANGE:
             raise ValueError()                                           # functions.py:360-361
         if (min_targ_p < min_src_p or min_targ_p < float(np.min(self.deltas.plev))) \
