@@ -11,8 +11,8 @@ What can and cannot be identical: the rounding STEPS are the same, but a float32
 geopotential sum (ulp 0.0078 m2/s2 = 0.009 Pa in ps) goes the other way whenever the float64 value in front of
 it sits closer to a rounding boundary than the ~1e-6 m2/s2 by which the fp32-stored deltas and vapour pressure
 of the CUDA path differ from the reference's float64 ones.  Measured on B200 over the 20 seeds below: 98.5 % of
-the columns get a bit-identical ps_pgw, 99.85 % lie within the north_star's 1e-2 Pa, the rest is off by two
-float32 ulps of ps (0.0156 Pa; three ulps in a handful of columns), and the per-iteration maximum of the
+the columns get a bit-identical ps_pgw, 99.86 % lie within the north_star's 1e-2 Pa, the rest is off by two to
+four float32 ulps of ps (0.0156 ... 0.031 Pa; profiles/r2_ref_dtypes.json), and the per-iteration maximum of the
 geopotential error moves by at most one ulp of the geopotential (0.0078 m2/s2).  The iteration count is
 therefore identical to the reference's whenever the threshold is further than that one ulp from every E_k --
 closer than that the reference's own count is decided by its rounding noise.  The default mode (float64
