@@ -63,7 +63,9 @@ def main():
     for i in range(20):
         r2 = eng.apply(sub, ERA_DATE, ignore_top_pressure_error=True)
         assert r2["n_iter"] == ref["n_iter"]
-    assert torch.equal(r2["PS"], res["PS"]) or float((r2["PS"] - res["PS"]).abs().max()) == 0.0
+    # (the first call speculated too many iterations and took the rewrite path, which rebuilds ps from the float32
+    # trajectory: one float32 ulp of ps at most)
+    assert float((r2["PS"] - res["PS"]).abs().max()) <= 2.0 ** -7
     print("rank %d rows %d..%d: n_iter %d == global oracle %d, fields within tolerance, exchange %s"
           % (rank, r0, r1, res["n_iter"], ref["n_iter"], eng.band_exchange), flush=True)
     dist.barrier()
