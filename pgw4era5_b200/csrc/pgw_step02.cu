@@ -181,6 +181,9 @@ regrid_rows_kernel(const float *__restrict__ src, float *__restrict__ dst, const
 // slots at 0.54 of the HBM peak; this one needs about a third of the instructions per point.
 // Same expressions as regrid_kernel, hence bit-identical.  `jt_begin, jt_end`: the band of target rows this
 // launch produces (dst holds only those rows): several GPUs split one variable by target latitude.
+#ifndef PGW_REGRID_F64
+#define PGW_REGRID_F64 0
+#endif
 #ifndef PGW_REGRID_CHUNK
 #define PGW_REGRID_CHUNK 32
 #endif
@@ -203,9 +206,18 @@ __device__ __forceinline__ void regrid_walk_body(const float *__restrict__ src, 
     const int nrow = jt_end - jt_begin, nchunk = (nrow + kRegridChunk - 1) / kRegridChunk;
     constexpr int SR = kRegridSrcRows, G = kRegridGroup;
     RegridQuad *const s_row = reinterpret_cast<RegridQuad *>(smem_raw);                 // [2][nx_s]
+#if PGW_REGRID_F64
+    // float64 staging: the landed rows are converted ONCE per chunk (10 conversions per thread instead of 2 per
+    // target row = 64), the latitude pass reads float64
+    double *const s_srcd = reinterpret_cast<double *>(s_row + 2 * nx_s);                // [SR + 2][nx_s]
+    RegridRow *const s_tab = reinterpret_cast<RegridRow *>(s_srcd + (SR + 2) * nx_s);   // [2][kRegridChunk]
+    float *const s_src = reinterpret_cast<float *>(s_tab + 2 * kRegridChunk);           // [SR][nx_s] landing buffer
+    const int2 *const s_chunk = reinterpret_cast<const int2 *>(s_src + SR * nx_s);      // [nchunk] (jmin, span)
+#else
     float *const s_src = reinterpret_cast<float *>(s_row + 2 * nx_s);                   // [2][SR + 2][nx_s]
     RegridRow *const s_tab = reinterpret_cast<RegridRow *>(s_src + 2 * (SR + 2) * nx_s);   // [2][kRegridChunk]
     const int2 *const s_chunk = reinterpret_cast<const int2 *>(s_tab + 2 * kRegridChunk);  // [nchunk] (jmin, span)
+#endif
     const int tid = threadIdx.x;
     const bool owner = tid < nx_t / VEC, col = tid < nx_s;
     const int u0 = ia[0], u1 = ib[0], u2 = ib[VEC - 1];
@@ -222,7 +234,11 @@ __device__ __forceinline__ void regrid_walk_body(const float *__restrict__ src, 
             pm0 = __ldg(polemean + 2 * ff); pm1 = __ldg(polemean + 2 * ff + 1);
             if (ch.y <= SR) {
                 const float *base = src + ((size_t)ff * ny_s + ch.x) * (size_t)nx_s + tid;
+#if PGW_REGRID_F64
+                float *d = s_src + tid;
+#else
                 float *d = s_src + b * (SR + 2) * nx_s + tid;
+#endif
 #pragma unroll
                 for (int r = 0; r < SR; ++r)
                     if (r < ch.y) __pipeline_memcpy_async(d + r * nx_s, base + (size_t)r * nx_s, 4);
@@ -235,12 +251,16 @@ __device__ __forceinline__ void regrid_walk_body(const float *__restrict__ src, 
     while (f < nfield) {
         const int2 ch = s_chunk[c];
         const bool staged = ch.y <= SR;
-        float *const ssrc = s_src + buf * (SR + 2) * nx_s;
         const int r_begin = c * kRegridChunk, r_end = min(r_begin + kRegridChunk, nrow);
+#if PGW_REGRID_F64
+        double *const ssrc = s_srcd;
+#else
+        float *const ssrc = s_src + buf * (SR + 2) * nx_s;
         if (col) {
             ssrc[SR * nx_s + tid] = pm0;                 // the two pole rows
             ssrc[(SR + 1) * nx_s + tid] = pm1;
         }
+#endif
         if (tid < kRegridChunk) {
             const int jt = jt_begin + min(r_begin + tid, r_end - 1);
             const int a = j0[jt], b = j1[jt];
@@ -260,6 +280,18 @@ __device__ __forceinline__ void regrid_walk_body(const float *__restrict__ src, 
         if (c >= nchunk) { c -= nchunk; ++f; }
         __pipeline_wait_prior(0);                   // this chunk's rows have landed (own copies; barrier: everyone's)
         __syncthreads();                            // parked rows and the row table are visible
+#if PGW_REGRID_F64
+        if (col) {
+            if (staged) {
+#pragma unroll
+                for (int r = 0; r < SR; ++r)
+                    if (r < ch.y) s_srcd[r * nx_s + tid] = (double)s_src[r * nx_s + tid];
+            }
+            s_srcd[SR * nx_s + tid] = (double)pc0;       // the two pole rows
+            s_srcd[(SR + 1) * nx_s + tid] = (double)pc1;
+        }
+        __syncthreads();                            // float64 rows visible, landing buffer free
+#endif
         prefetch(f, c, buf ^ 1);                    // in flight while this chunk is computed; the last readers of
                                                     // that half passed the barrier above
         const RegridRow *tab = s_tab + buf * kRegridChunk;
@@ -273,7 +305,7 @@ __device__ __forceinline__ void regrid_walk_body(const float *__restrict__ src, 
                     const RegridRow t = tab[k];
                     double a, b;
                     if (staged) {
-                        a = (double)ssrc[t.off_a + tid]; b = (double)ssrc[t.off_b + tid];
+                        a = (double)ssrc[t.off_a + tid]; b = (double)ssrc[t.off_b + tid];   // (no conversion with F64 staging)
                     } else {
                         auto at = [&](int o) { return (double)(o == -1 ? pc0 : (o == -2 ? pc1 : __ldg(fld + o + tid))); };
                         a = at(t.off_a); b = at(t.off_b);
@@ -357,9 +389,16 @@ regrid_walk_kernel(const float *__restrict__ src, float *__restrict__ dst, const
                    const int *__restrict__ i0, const int *__restrict__ i1, const double *__restrict__ wx) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int nrow = jt_end - jt_begin, nchunk = (nrow + kRegridChunk - 1) / kRegridChunk;
+#if PGW_REGRID_F64
+    int2 *const s_chunk = reinterpret_cast<int2 *>(smem_raw + sizeof(RegridQuad) * 2 * nx_s +
+                                                   sizeof(double) * (kRegridSrcRows + 2) * nx_s +
+                                                   sizeof(RegridRow) * 2 * kRegridChunk +
+                                                   sizeof(float) * kRegridSrcRows * nx_s);
+#else
     int2 *const s_chunk = reinterpret_cast<int2 *>(smem_raw + sizeof(RegridQuad) * 2 * nx_s +
                                                    sizeof(float) * 2 * (kRegridSrcRows + 2) * nx_s +
                                                    sizeof(RegridRow) * 2 * kRegridChunk);
+#endif
     const int tid = threadIdx.x;
     const bool owner = tid < nx_t / VEC;
     // ---- per launch: span of source rows of every chunk; longitude brackets of this thread
@@ -501,8 +540,14 @@ int pgw_regrid_bilinear_band_f32(const float *src, float *dst, const float *pole
     const bool walk_ok = (vec ? nx_t / 4 : nx_t) <= 384 && nx_s <= 384 && nfield * (long long)nchunk < (1LL << 31) &&
                          nchunk <= 4096 && !(force && (!strcmp(force, "rows") || !strcmp(force, "generic")));
     if (walk_ok) {
+#if PGW_REGRID_F64
+        const size_t smem = sizeof(RegridQuad) * 2 * (size_t)nx_s + sizeof(RegridRow) * 2 * kRegridChunk +
+                            sizeof(double) * (kRegridSrcRows + 2) * (size_t)nx_s +
+                            sizeof(float) * kRegridSrcRows * (size_t)nx_s + sizeof(int2) * (size_t)nchunk;
+#else
         const size_t smem = sizeof(RegridQuad) * 2 * (size_t)nx_s + sizeof(RegridRow) * 2 * kRegridChunk +
                             sizeof(float) * 2 * (kRegridSrcRows + 2) * (size_t)nx_s + sizeof(int2) * (size_t)nchunk;
+#endif
         const long long nitem = nfield * (long long)nchunk;
         long long g = nitem < 148LL * 5 ? nitem : 148LL * 5;
         if (smem > 48 * 1024) {
