@@ -169,6 +169,9 @@ def _copy_range(fd_in, fd_out, off, count):
         count -= n
 
 
+_WRITE_PIECE = 64 << 20
+
+
 def _write_raw(raw, names, inp_path, out_path, host_out, pool=None):
     """The output file = the input file with the eight updated fields replaced (step_03:367-378): the
     bytes in between are copied file to file, the fields come straight from the (big-endian) host buffers.
@@ -177,11 +180,11 @@ def _write_raw(raw, names, inp_path, out_path, host_out, pool=None):
     fd_in = os.open(inp_path, os.O_RDONLY)
     fd_out = os.open(out_path, os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o644)
 
-    def put(off, nbytes, key):
+    def put(off, nbytes, key, lo=0, hi=None):
         mv = memoryview(host_out[key].numpy()).cast("B")
-        done = 0
-        while done < nbytes:
-            done += os.pwrite(fd_out, mv[done:nbytes], off + done)
+        done, end = lo, nbytes if hi is None else hi
+        while done < end:
+            done += os.pwrite(fd_out, mv[done:end], off + done)
 
     try:
         size = os.fstat(fd_in).st_size
@@ -189,7 +192,9 @@ def _write_raw(raw, names, inp_path, out_path, host_out, pool=None):
         jobs, pos = [], 0
         for off, nbytes, key in segs:
             jobs.append((_copy_range, (fd_in, fd_out, pos, off - pos)))
-            jobs.append((put, (off, nbytes, key)))
+            # a 3-D field of a global file is 570 MB: cut into pieces so that all writer threads stay busy
+            for lo in range(0, nbytes, _WRITE_PIECE):
+                jobs.append((put, (off, nbytes, key, lo, min(nbytes, lo + _WRITE_PIECE))))
             pos = off + nbytes
         jobs.append((_copy_range, (fd_in, fd_out, pos, size - pos)))
         if pool is None:
@@ -260,7 +265,7 @@ def pgw_for_era5_files(steps, delta_input_dir, ignore_top_pressure_error, debug_
                     return False
     # the raw path is a copy between the page cache and pinned memory: a few threads per direction
     # (pread / pwrite release the GIL) move the fields of one file side by side
-    n_io = max(1, min(4, (os.cpu_count() or 2) // 2))
+    n_io = max(1, min(8, (os.cpu_count() or 2) // 2))
     rpool, wpool = ThreadPoolExecutor(n_io), ThreadPoolExecutor(n_io)
 
     def reader():

@@ -36,7 +36,7 @@ def breakdown(a, inp, dd, whens, fbytes):
     pipe = HostPipeline(eng, a.ny, a.nx)
     h_in, h_out = pipe.alloc_host_inputs(), pipe.alloc_host_outputs()
     raw = S3._raw_layout(path, names, h_in)
-    pool = ThreadPoolExecutor(4)
+    pool = ThreadPoolExecutor(8)
     out = {}
 
     def best(fn, reps=3):
