@@ -60,7 +60,8 @@ parked / both sweep loops on top of the packing (1.32 / 1.35 / 1.46 ms), five ri
 over two).  Regrid kernel: 8.70 (round-1 rows kernel) -> 7.00 (walking kernel: staged source rows, row table, uniform
 three-column pattern) -> 6.51 (4 rows per barrier, cp.async staging, 16-row chunks) -> 6.22 (32-row chunks); dropped: float64
 staging (6.46), float64 staging + software-pipelined passes (7.88), 2 CTAs/SM (8.2).  Smoothing: 1.04 -> 1.006 (8 loads in
-flight per thread); two points per thread 1.31, constant-memory tables 1.50, other launch shapes 1.00-1.05.
+flight per thread) -> 0.953 (cp.async ring, 16 stamps ahead); two points per thread 1.31, constant-memory tables 1.50, other
+launch shapes 0.98-1.05; read pass alone 0.58 ms, write pass alone 0.42 ms; same GB/s for 8 plevs (2 MB rows) as for 19.
 
 Tools added: `sass_hist.py` (static opcode histogram / loop sizes of a kernel), `make_summary_r2.py` (this file),
 `gpu_r2*.sh` (the GPU calls of this round).
