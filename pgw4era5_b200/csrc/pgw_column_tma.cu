@@ -44,6 +44,13 @@ namespace pgw {
 #ifndef PGW_X2
 #define PGW_X2 1
 #endif
+// PGW_UNIFORM_TOP: levels whose full-level pressure does not depend on ps (bkm == 0: the pure pressure levels at
+// the top of the model) have a column-independent walker position and interpolation weight; they are tabulated once
+// per CTA (with the very instructions the per-column walk uses, hence bit-identical) and the streamed pairs made of
+// such levels skip the lg2, the weight multiply, the step tests and the exact-hit selects.
+#ifndef PGW_UNIFORM_TOP
+#define PGW_UNIFORM_TOP 0
+#endif
 #ifndef PGW_TMA_SLOTS
 #define PGW_TMA_SLOTS 4
 #endif
@@ -97,7 +104,14 @@ pgw_column_tma_kernel(const __grid_constant__ pgw_timestep_args a, const __grid_
     float *const s_plev = reinterpret_cast<float *>(m0p + np);                     // [K] ascending
     float *const s_inv_plev = s_plev + K;                                          // [K]
     float *const s_inv_w = s_inv_plev + K;                                         // [K] 1/log2(p[j+1]/p[j])
+#if PGW_UNIFORM_TOP
+    const int K3 = 3 * K + ((3 * K) & 1), Lp = L + (L & 1);
+    float *const s_ut = s_plev + K3;                                               // [L] weight of a uniform level
+    int *const s_un = reinterpret_cast<int *>(s_ut + Lp);                          // [L] its node (lo) index
+    uint64_t *const bar_full = reinterpret_cast<uint64_t *>(s_un + Lp);
+#else
     uint64_t *const bar_full = reinterpret_cast<uint64_t *>(s_plev + 3 * K + ((3 * K) & 1));
+#endif
     uint64_t *const bar_done = bar_full + kTmaSlots;
     const double2 *const s_hl = hl0 - lst;      // indexed by the half level, l >= lst
     const float2 *const s_m = m0p - lst;        // indexed by the full level, l >= lst
@@ -120,6 +134,18 @@ pgw_column_tma_kernel(const __grid_constant__ pgw_timestep_args a, const __grid_
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+#if PGW_UNIFORM_TOP
+    // walker position and weight of the levels whose pressure is akm alone, by the instructions of walk()
+    for (int l = tid; l < L; l += NT + 32) {
+        const float2 m = tp.m[l];
+        int nd = -1;
+        for (int k = K - 1; k >= 0; --k)
+            if (s_plev[k] <= m.x) { nd = k; break; }
+        s_un[l] = nd;
+        s_ut[l] = nd >= 0 ? fast_lg2(m.x * s_inv_plev[nd]) * s_inv_w[nd] : 0.0f;
+    }
+    __syncthreads();
+#endif
 
     const uint32_t n = (uint32_t)a.ncol;
     const int npairs = (L + 1) >> 1, np1 = np >> 1;     // level pairs in total / parked (np is even)
@@ -349,6 +375,36 @@ pgw_column_tma_kernel(const __grid_constant__ pgw_timestep_args a, const __grid_
         return d;
     };
     auto walk = [&](float p) { step_to(p); return interp(p); };
+#if PGW_UNIFORM_TOP
+    // the same for a level with a column-independent pressure: node and weight from the CTA's table
+    auto walk_uniform = [&](int l) {
+        const int nd = s_un[l];
+        while (w_lo > nd) {
+            if (stale) refresh();
+            const F4 hi = x_lo;
+            --w_lo;
+            if (w_lo >= 0) {
+                w_p_lo = s_plev[w_lo]; w_inv_p_lo = s_inv_plev[w_lo]; w_inv_w = s_inv_w[w_lo];
+                x_lo = nb;
+                x_d = F4{hi.x - x_lo.x, hi.y - x_lo.y, hi.z - x_lo.z, hi.w - x_lo.w};
+                stale = true;
+            } else {
+                x_d = F4{0.f, 0.f, 0.f, 0.f}; w_inv_w = 0.0f; w_p_lo = 0.0f; w_inv_p_lo = 1.0f;
+            }
+        }
+        const float t = s_ut[l];
+        Dlt d;
+        if (t == 0.0f) {                     // CTA-uniform: exact node hit or constant extrapolation
+            d.ta = x_lo.x; d.hur = x_lo.y; d.ua = x_lo.z; d.va = x_lo.w;
+        } else {
+            const float2 tt = make_float2(t, t);
+            const float2 ab = __ffma2_rn(tt, make_float2(x_d.x, x_d.y), make_float2(x_lo.x, x_lo.y));
+            const float2 cd = __ffma2_rn(tt, make_float2(x_d.z, x_d.w), make_float2(x_lo.z, x_lo.w));
+            d.ta = ab.x; d.hur = ab.y; d.ua = cd.x; d.va = cd.y;
+        }
+        return d;
+    };
+#endif
     auto sfc_override = [&](float p, Dlt &d) {
         if (bot_on) {
             if (p > b_p1) {
@@ -555,8 +611,14 @@ pgw_column_tma_kernel(const __grid_constant__ pgw_timestep_args a, const __grid_
 #else
         const float p0 = fmaf(ps_f, mm0.y, mm0.x), p1 = fmaf(ps_f, mm1.y, mm1.x);
 #endif
+#if PGW_UNIFORM_TOP
+        Dlt d0, d1;
+        if (!parked && mm0.y == 0.0f && mm1.y == 0.0f) { d0 = walk_uniform(l); d1 = walk_uniform(l - 1); }
+        else { d0 = walk(p0); d1 = walk(p1); }
+#else
         Dlt d0 = walk(p0);
         Dlt d1 = walk(p1);
+#endif
         if (stale) refresh();
         if (!ready) mbar_wait(bar_full + (j % kTmaSlots), (j / kTmaSlots) & 1);
         const float t0 = sl[NT], q0 = sl[3 * NT], u0 = sl[5 * NT], v0 = sl[7 * NT];    // row 1: level l
@@ -650,12 +712,15 @@ namespace {
 
 using pgw::kColumnThreads;
 
-size_t column_smem_tma(int nplev, int np) {
+size_t column_smem_tma(int nplev, int np, int nlev) {
     const int nt = kColumnThreads;
     size_t b = sizeof(float) * (size_t)pgw::kTmaSlots * 8 * nt +            // pair ring
                (size_t)np * nt * (2 * sizeof(float)) +                      // stash
                sizeof(double) * 2 * (size_t)(np + 1) + sizeof(float) * 2 * (size_t)np;
     b += sizeof(float) * (size_t)(3 * nplev + ((3 * nplev) & 1));
+#if PGW_UNIFORM_TOP
+    b += 2 * sizeof(float) * (size_t)(nlev + (nlev & 1));
+#endif
     b += sizeof(uint64_t) * 2 * pgw::kTmaSlots;
     return b;
 }
@@ -729,7 +794,7 @@ bool pgw_tma_eligible(const pgw_timestep_args *a, int lst_generic, int *lst_tma,
     for (const void *p : f) if (!aligned16(p)) return false;
     if (!encode_tiled()) return false;
     *lst_tma = lst_even;
-    *smem = column_smem_tma(a->nplev, a->nlev - lst_even);
+    *smem = column_smem_tma(a->nplev, a->nlev - lst_even, a->nlev);
     return true;
 }
 
