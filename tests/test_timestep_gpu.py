@@ -419,3 +419,25 @@ def test_staged_path_matches_executed_reference(tag, name, value):
     tol = dict(TOL)
     tol.pop("delta_ps")
     _vs_reference(G, tag, res, tol)
+
+
+def test_no_soil_levels_and_many_soil_levels():
+    """Edge cases of the soil block (step_03:139-146): a file without soil levels, and the maximum the ABI carries
+    (PGW_MAX_SOIL = 16)."""
+    from pgw4era5_b200 import _native as N
+    era, deltas = make_case(9, 32, 41)
+    ref_T_SKIN = run_oracle(era, deltas)["T_SKIN"]
+    for nsoil in (0, N.PGW_MAX_SOIL):
+        e = dict(era)
+        e["soil1"] = np.linspace(0.01, 3.0, nsoil)
+        e["T_SO"] = era["T_SO"][:, :1].repeat(1, max(nsoil, 1), 1, 1)[:, :nsoil].contiguous() - \
+            0.1 * torch.arange(nsoil, dtype=torch.float32).reshape(1, nsoil, 1, 1)
+        ref = run_oracle(e, deltas)
+        res, _ = _apply(e, deltas)
+        assert tuple(res["T_SO"].shape[:2]) == (1, nsoil)
+        _check(res, ref)
+        np.testing.assert_array_equal(ref["T_SKIN"], ref_T_SKIN)         # the soil block does not touch the rest
+    with pytest.raises(ValueError, match="soil"):
+        e = dict(era)
+        e["soil1"] = np.linspace(0.01, 3.0, N.PGW_MAX_SOIL + 1)
+        _engine(e, deltas)
