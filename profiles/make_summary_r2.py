@@ -7,6 +7,7 @@ L = lambda f: json.load(open(os.path.join(P, f)))
 m = L('r2_multigpu.json')
 b1, ref, b2, b8 = m['n1']['bench'], m['n1']['reference_arm'], m['n2']['bench'], m['n8']['bench']
 p8, p2 = m['n8']['bench_with_peer_memory_band_exchange'], m['n2']['bench_with_peer_memory_band_exchange']
+b4 = m['n4']['bench']
 s2, f, sf, rd, pg = L('r2_step02.json'), L('r2_files.json'), L('r2_step02_files.json'), L('r2_ref_dtypes.json'), L('r2_parity_global.json')
 mx = lambda k: max(c['maxerr'][k] for c in pg['cases'])
 sb = m['n8']['step02_banded']
@@ -30,12 +31,12 @@ inputs cycling through 4 distinct device-resident timesteps (2.3 GB each >> 126 
 | warp instructions per launch / issue slots active | 839 M / 57 % | 796 M / 56 % | `r2_column_kernel.md` |
 | host time per submit; `ms_per_step - kernel_ms` | - ; 0.031 ms | {b1['config']['host_us_per_submit']:.0f} us; {b1['ms_per_step']-b1['roofline']['kernel_ms']:.3f} ms | bench line |
 | `e2e` (host buffers, copies inside the timing), 1 GPU | 19.8 | {b1['e2e']['value']:.1f} timesteps/s = {b1['e2e']['frac_of_link']:.2f} x the measured link bound ({b1['e2e']['link_bound']['gb_per_s_per_direction_per_gpu']:.1f} GB/s per direction with both directions busy) | same |
-| timesteps/s, 2xB200 | 1 524 | {b2['value']:.0f} | torchrun, 20 steps |
+| timesteps/s, 2xB200 / 4xB200 | 1 524 / 3 042 | {b2['value']:.0f} / {b4['value']:.0f} | torchrun, 20 steps |
 | timesteps/s, 8xB200; efficiency vs 8 x N=1 | 5 562; 0.91 | **{p8['value']:.0f}**; {p8['value']/8/b1['value']:.3f} | torchrun, 20 steps |
 | `ms_per_step - kernel_ms` at N = 8 | 0.157 ms | {b8['ms_per_step']-b8['roofline']['kernel_ms']:.3f} ms | same |
 | NCCL broadcast of the climatology (5.03 GB), 2 / 8 GPUs | 355 / 1 068 ms (8 collectives, incl. NCCL start-up) | {b2['config']['broadcast']['ms']:.1f} ms ({b2['config']['broadcast']['gb_per_s']:.0f} GB/s) / {b8['config']['broadcast']['ms']:.1f} ms ({b8['config']['broadcast']['gb_per_s']:.0f} GB/s), one collective | `config.broadcast` |
-| `e2e` at N = 2 / 8 (sum over ranks) | 22.8 / 28.2 | {b2['e2e']['value']:.1f} / {b8['e2e']['value']:.1f} = {b2['e2e']['frac_of_link']:.2f} / {b8['e2e']['frac_of_link']:.2f} x the platform bound measured bare ({b2['e2e']['link_bound']['gb_per_s_per_direction_per_gpu']:.1f} / {b8['e2e']['link_bound']['gb_per_s_per_direction_per_gpu']:.1f} GB/s per direction and GPU when all ranks copy both ways at once) | `e2e.link_bound`, `tests/multigpu_pcie.py` |
-| one global snapshot in latitude bands, plev37, thresh 1e-3 (BASELINE configs[4]), 8 / 2 GPUs | 0.65 / 1.15 ms | **{p8['latband']['ms_per_snapshot']:.3f}** / {p2['latband']['ms_per_snapshot']:.3f} ms with the exchange fused over peer memory ({p8['latband']['nccl_form_of_the_exchange']['ms_per_snapshot']:.3f} / {p2['latband']['nccl_form_of_the_exchange']['ms_per_snapshot']:.3f} with one NCCL all-reduce); band kernels alone {p8['latband']['ms_per_snapshot_band_kernels_only']:.3f} ms; {p8['latband']['n_iter']} iterations = whole grid; band vs whole-grid fields max abs diff {p8['latband']['band_vs_whole_grid_max_abs_diff']} | `config.latband` |
+| `e2e` at N = 2 / 4 / 8 (sum over ranks) | 22.8 / 22.0 / 28.2 | {b2['e2e']['value']:.1f} / {b4['e2e']['value']:.1f} / {b8['e2e']['value']:.1f} = {b2['e2e']['frac_of_link']:.2f} / {b4['e2e']['frac_of_link']:.2f} / {b8['e2e']['frac_of_link']:.2f} x the platform bound measured bare ({b2['e2e']['link_bound']['gb_per_s_per_direction_per_gpu']:.1f} / {b4['e2e']['link_bound']['gb_per_s_per_direction_per_gpu']:.1f} / {b8['e2e']['link_bound']['gb_per_s_per_direction_per_gpu']:.1f} GB/s per direction and GPU when all ranks copy both ways at once) | `e2e.link_bound`, `tests/multigpu_pcie.py` |
+| one global snapshot in latitude bands, plev37, thresh 1e-3 (BASELINE configs[4]), 8 / 2 GPUs | 0.65 / 1.15 ms | **{p8['latband']['ms_per_snapshot']:.3f}** / {p2['latband']['ms_per_snapshot']:.3f} ms with the exchange fused over peer memory ({p8['latband']['nccl_form_of_the_exchange']['ms_per_snapshot']:.3f} / {p2['latband']['nccl_form_of_the_exchange']['ms_per_snapshot']:.3f} with one NCCL all-reduce); band kernels alone {p8['latband']['ms_per_snapshot_band_kernels_only']:.3f} ms; 4 GPUs: {b4['config']['latband']['ms_per_snapshot']:.3f} ms; {p8['latband']['n_iter']} iterations = whole grid; band vs whole-grid fields max abs diff {p8['latband']['band_vs_whole_grid_max_abs_diff']} | `config.latband` |
 | CPU arm: oracle port on 16 host cores, IterMP-driven | 0.105 (17.75 % sample) | {ref['value']:.4f} timesteps/s ({ref['config']['sampled_fraction_of_timestep']:.3f} of a timestep per step) | `bench.py --impl reference` |
 | step_02 regridding, one 3-D daily variable (28.8 GB out) | 8.75 ms (0.54) | **{s2['regridding']['ms']:.2f} ms = {s2['regridding']['achieved_gbs']:.0f} GB/s ({s2['regridding']['frac_of_peak']:.3f} of peak)** | `tests/bench_step02.py` |
 | step_02 smoothing, one 3-D daily variable | 1.05 ms (0.53) | {s2['smoothing']['ms']:.3f} ms ({s2['smoothing']['frac_of_peak']:.3f}) | same |
