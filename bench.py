@@ -79,6 +79,10 @@ class ClockSampler:
         self.t0 = time.time()
 
     def mark_stop(self):
+        """End of a timed region; may be called again: the window then extends to the end of the later region
+        (device-resident steps first, the e2e leg after it), the first end is kept for `samples_in_region`."""
+        if self.t1 is not None and not hasattr(self, "t1_first"):
+            self.t1_first = self.t1
         self.t1 = time.time()
 
     def summary(self):
@@ -100,6 +104,8 @@ class ClockSampler:
                     continue
                 rows.append((ts, r))
         inside = [r for ts, r in rows if self.t0 is not None and self.t0 - 0.05 <= ts <= self.t1 + 0.15]
+        t1a = getattr(self, "t1_first", self.t1)
+        first = [r for ts, r in rows if self.t0 is not None and self.t0 - 0.05 <= ts <= t1a + 0.15]
         use = inside if inside else [r for _, r in rows]
         num = lambda x: float(x) if x.replace(".", "", 1).isdigit() else None
         sm = [num(r[2]) for r in use if num(r[2]) is not None]
@@ -111,7 +117,10 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(use), "samples_in_region": len(inside)}
+                "reasons": sorted(reasons), "samples": len(use), "samples_in_region": len(first),
+                "samples_in_timed_regions": len(inside),
+                "window": "device-resident timed region + e2e timed region" if hasattr(self, "t1_first")
+                          else "device-resident timed region"}
 
 
 # --------------------------------------------------------------------------- CPU arm
@@ -481,6 +490,8 @@ def run_ours(a):
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_val = world * a.e2e_steps / float(t.item())
+        if sampler:
+            sampler.mark_stop()
         h2d_b, d2h_b = pipe.h2d_bytes, pipe.d2h_bytes
         del pipe, hin, houts
         # the platform's bound for this pipeline: bare pinned copies of the same sizes, both directions at once,
